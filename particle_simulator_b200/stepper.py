@@ -1,0 +1,213 @@
+"""ctypes binding of libpsim_b200.so (include/psim_b200.h): the B200 particle stepper.
+
+`Stepper` mirrors the reference's `Kernel` object (cuda_simulator/src/kernel.cuh:22-132) the way its
+main loop uses it (cuda_simulator/src/cuda_simulator.cu:7-38):
+
+    reference                                   here
+    kernel_prepare_frame + kernel.write(id)     Stepper.upload(frame)
+    kernel.write_metadata(id)                   Stepper.set_metadata(meta)
+    kernel.run_async(src, dst)                  Stepper.run_frame_async()
+    kernel.sync()                               Stepper.sync()
+    kernel.read(id) + frame_compact             Stepper.download(frame)
+
+There is no CPU fallback: if the CUDA library is missing or no B200 is present, construction raises.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+
+import numpy as np
+
+from . import _build
+from .frame import METADATA_DTYPE, FrameBuffer
+
+SCHEDULE_REFERENCE = 0
+SCHEDULE_NATIVE = 1
+
+_lib = None
+
+
+class PsimError(RuntimeError):
+    pass
+
+
+class CConfig(ctypes.Structure):
+    _fields_ = [
+        ("grid_x_log2", ctypes.c_uint32),
+        ("grid_y_log2", ctypes.c_uint32),
+        ("max_particles", ctypes.c_uint32),
+        ("schedule", ctypes.c_uint32),
+        ("rebin_every", ctypes.c_uint32),
+        ("device", ctypes.c_int32),
+        ("use_graph", ctypes.c_uint32),
+        ("_reserved", ctypes.c_uint32 * 5),
+    ]
+
+
+def lib() -> ctypes.CDLL:
+    """Load libpsim_b200.so; raises if it has not been built (the product has no other path)."""
+    global _lib
+    if _lib is None:
+        path = _build.LIB_PSIM
+        if not os.path.exists(path):
+            raise PsimError(f"{path} is missing: run `python -m particle_simulator_b200._build` "
+                            "(there is no CPU fallback for the stepper)")
+        L = ctypes.CDLL(path)
+        vp = ctypes.c_void_p
+        L.psim_default_config.restype = CConfig
+        L.psim_default_config.argtypes = []
+        L.psim_create.restype = ctypes.c_int
+        L.psim_create.argtypes = [ctypes.POINTER(CConfig), ctypes.POINTER(vp)]
+        L.psim_destroy.restype = None
+        L.psim_destroy.argtypes = [vp]
+        L.psim_last_error.restype = ctypes.c_char_p
+        L.psim_last_error.argtypes = [vp]
+        for name, args in {
+            "psim_set_stream": [vp, vp],
+            "psim_upload_frame": [vp, vp],
+            "psim_upload_device": [vp, vp, vp, ctypes.c_uint32],
+            "psim_set_metadata": [vp, vp],
+            "psim_get_metadata": [vp, vp],
+            "psim_run_frame_async": [vp],
+            "psim_step_async": [vp, ctypes.c_uint32],
+            "psim_rebin_async": [vp],
+            "psim_snapshot_async": [vp],
+            "psim_sync": [vp],
+            "psim_download_frame": [vp, vp],
+            "psim_get_cell_start": [vp, vp],
+            "psim_enable_step_timing": [vp, ctypes.c_int],
+            "psim_get_step_timing": [vp, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_uint64)],
+            "psim_device_state": [vp, ctypes.POINTER(vp), ctypes.POINTER(vp), ctypes.POINTER(vp), ctypes.POINTER(vp)],
+        }.items():
+            getattr(L, name).restype = ctypes.c_int
+            getattr(L, name).argtypes = args
+        L.psim_particle_count.restype = ctypes.c_uint32
+        L.psim_cell_count.restype = ctypes.c_uint32
+        for name in ("psim_steps_executed", "psim_rebins_executed", "psim_kernel_launches"):
+            getattr(L, name).restype = ctypes.c_uint64
+        for name in ("psim_particle_count", "psim_cell_count", "psim_steps_executed", "psim_rebins_executed",
+                     "psim_kernel_launches"):
+            getattr(L, name).argtypes = [vp]
+        _lib = L
+    return _lib
+
+
+class Stepper:
+    def __init__(self, grid_log2: tuple[int, int] = (6, 6), max_particles: int = 65536,
+                 schedule: int = SCHEDULE_REFERENCE, rebin_every: int = 0, device: int = -1,
+                 use_graph: bool = False):
+        L = lib()
+        cfg = L.psim_default_config()
+        cfg.grid_x_log2, cfg.grid_y_log2 = grid_log2
+        cfg.max_particles = max_particles
+        cfg.schedule = schedule
+        cfg.rebin_every = rebin_every
+        cfg.device = device
+        cfg.use_graph = 1 if use_graph else 0
+        self._h = ctypes.c_void_p()
+        rc = L.psim_create(ctypes.byref(cfg), ctypes.byref(self._h))
+        if rc != 0:
+            self._h = ctypes.c_void_p()
+            raise PsimError(f"psim_create failed ({rc}): {L.psim_last_error(None).decode()}")
+        self.grid_log2 = tuple(grid_log2)
+        self.max_particles = max_particles
+
+    # -- plumbing ----------------------------------------------------------------------------
+    def _check(self, rc: int) -> None:
+        if rc != 0:
+            raise PsimError(f"psim error {rc}: {lib().psim_last_error(self._h).decode()}")
+
+    def close(self) -> None:
+        if getattr(self, "_h", None) and self._h.value:
+            lib().psim_destroy(self._h)
+            self._h = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    # -- the Kernel-shaped API ---------------------------------------------------------------
+    def set_stream(self, cuda_stream: int | None) -> None:
+        self._check(lib().psim_set_stream(self._h, ctypes.c_void_p(cuda_stream or 0)))
+
+    def upload(self, frame: FrameBuffer) -> None:
+        self._check(lib().psim_upload_frame(self._h, frame.ptr))
+
+    def upload_device(self, metadata: np.ndarray, d_particles: int, count: int) -> None:
+        meta = np.ascontiguousarray(metadata, dtype=METADATA_DTYPE)
+        self._check(lib().psim_upload_device(self._h, ctypes.c_void_p(meta.ctypes.data),
+                                             ctypes.c_void_p(d_particles), count))
+
+    def set_metadata(self, metadata: np.ndarray) -> None:
+        meta = np.ascontiguousarray(metadata, dtype=METADATA_DTYPE)
+        self._check(lib().psim_set_metadata(self._h, ctypes.c_void_p(meta.ctypes.data)))
+
+    def get_metadata(self) -> np.ndarray:
+        meta = np.zeros((), dtype=METADATA_DTYPE)
+        self._check(lib().psim_get_metadata(self._h, ctypes.c_void_p(meta.ctypes.data)))
+        return meta
+
+    def run_frame_async(self) -> None:
+        self._check(lib().psim_run_frame_async(self._h))
+
+    def step_async(self, steps: int = 1) -> None:
+        self._check(lib().psim_step_async(self._h, steps))
+
+    def rebin_async(self) -> None:
+        self._check(lib().psim_rebin_async(self._h))
+
+    def snapshot_async(self) -> None:
+        self._check(lib().psim_snapshot_async(self._h))
+
+    def sync(self) -> None:
+        self._check(lib().psim_sync(self._h))
+
+    def download(self, frame: FrameBuffer | None = None) -> FrameBuffer:
+        if frame is None:
+            frame = FrameBuffer(max(self.particle_count, 1))
+        frame.count = frame.capacity
+        self._check(lib().psim_download_frame(self._h, frame.ptr))
+        return frame
+
+    # -- introspection -----------------------------------------------------------------------
+    @property
+    def particle_count(self) -> int:
+        return int(lib().psim_particle_count(self._h))
+
+    @property
+    def cell_count(self) -> int:
+        return int(lib().psim_cell_count(self._h))
+
+    @property
+    def steps_executed(self) -> int:
+        return int(lib().psim_steps_executed(self._h))
+
+    @property
+    def rebins_executed(self) -> int:
+        return int(lib().psim_rebins_executed(self._h))
+
+    @property
+    def kernel_launches(self) -> int:
+        return int(lib().psim_kernel_launches(self._h))
+
+    def cell_start(self) -> np.ndarray:
+        out = np.zeros(self.cell_count + 1, dtype=np.uint32)
+        self._check(lib().psim_get_cell_start(self._h, ctypes.c_void_p(out.ctypes.data)))
+        return out
+
+    def enable_step_timing(self, enable: bool = True) -> None:
+        self._check(lib().psim_enable_step_timing(self._h, 1 if enable else 0))
+
+    def step_timing(self) -> tuple[float, int]:
+        ms, n = ctypes.c_double(), ctypes.c_uint64()
+        self._check(lib().psim_get_step_timing(self._h, ctypes.byref(ms), ctypes.byref(n)))
+        return ms.value, n.value
