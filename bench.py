@@ -1,0 +1,322 @@
+#!/usr/bin/env python
+"""bench.py -- particle-updates/s of the per-timestep update at 10M particles (BASELINE.json).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+A bench "step" is one FRAME of the hot path: metadata.steps_per_frame = 100 leapfrog steps on the
+reference's step / re-bin schedule (101 steps and 6 re-bins are executed, kernel_bucket.cuh:181-206).
+  value        particle-updates/s with the state resident in HBM (frames chained on the device)
+  e2e          the same metric through the reference-facing C ABI with HOST frames: every step
+               uploads the scene (psim_upload_frame, H2D from pinned memory + binning), runs a frame
+               and downloads the compacted result (psim_download_frame, D2H)
+  roofline     step kernel only: 40 B per particle-update (20 B record in + 20 B out)
+               over the measured HBM copy bandwidth (MEASURED_PEAKS.json)
+  cpu_baseline the reference's own CPU implementation (oracle/_ref, compiled from /root/reference)
+               on this box's host cores, on a bounded sample of the same workload
+`--impl reference` times that CPU implementation alone and prints the same line shape.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+REPO = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, REPO)
+
+ALGO_BYTES_PER_UPDATE = 40
+STEPS_PER_FRAME = 100
+
+
+def measured_hbm_peak() -> tuple[float, str]:
+    path = os.path.join(REPO, "MEASURED_PEAKS.json")
+    try:
+        with open(path) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def recorded_traffic() -> float | None:
+    """dram bytes per launch of the step kernel from the committed ncu capture, if there is one."""
+    try:
+        with open(os.path.join(REPO, "profiles", "step_kernel_traffic.json")) as f:
+            return float(json.load(f)["dram_bytes_per_launch"])
+    except Exception:
+        return None
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons while the timed region runs (B200_PROFILING.md)."""
+
+    QUERY = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index = index
+        self.rows: list[list[str]] = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits",
+                 "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self) -> dict:
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx.append(float(r[1]))
+                for k, name in enumerate(names):
+                    if r[3 + k].lower().startswith("active"):
+                        reasons.add(name)
+            except Exception:
+                pass
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def pinned_storage(nbytes: int):
+    import torch
+
+    t = torch.empty(nbytes, dtype=torch.uint8, pin_memory=True)
+    return t, t.numpy()
+
+
+def run_reference(args, rank: int, world: int) -> None:
+    """The reference's CPU implementation of the path (Device::CpuThreadPool, all host threads) from
+    oracle/_ref on the same 10M-particle workload; a step = one frame of `ref_steps` leapfrog steps."""
+    if rank != 0:
+        return
+    from oracle.oracle import RefOracle, ref_available
+    from particle_simulator_b200 import workloads
+    from particle_simulator_b200.frame import DEVICE_CPU_THREAD_POOL
+
+    if not ref_available(11, 11):
+        print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/libref_11_11.so has not been built"}))
+        return
+    wl = workloads.config_10m_solid()
+    ref = RefOracle(11, 11)
+    wl.frame.metadata["device"] = DEVICE_CPU_THREAD_POOL
+    wl.frame.metadata["steps_per_frame"] = args.ref_steps
+    ref.prepare(wl.frame)
+    executed = schedule_steps(args.ref_steps)
+    for _ in range(args.warmup):
+        ref.run_frame()
+    t = 0.0
+    for _ in range(args.steps):
+        t += ref.run_frame()
+    n = wl.particles
+    value = n * executed * args.steps / t
+    sample = (f"{args.steps} frames of {executed} leapfrog steps (steps_per_frame={args.ref_steps}) on the full "
+              f"{n}-particle scene, Device::CpuThreadPool")
+    line = {
+        "impl": "reference", "metric": "particle-updates/sec at 10M particles", "value": value,
+        "unit": "particle-updates/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1e3 * t / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": wl.name, "description": wl.description, "particles": n,
+                   "steps_per_frame": args.ref_steps, "leapfrog_steps_per_bench_step": executed},
+        "cpu_baseline": {"value": value, "unit": "particle-updates/s", "cores": ref.hardware_threads,
+                         "kind": "reference", "sample": sample},
+        "e2e": {"value": value, "unit": "particle-updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+def schedule_steps(S: int) -> int:
+    """Steps the reference schedule executes for steps_per_frame = S (kernel_bucket.cuh:181-206)."""
+    steps, cd = 1, 0
+    while steps < S:
+        if cd <= 0:
+            cd, steps = 15, steps + 1
+        else:
+            cd, steps = cd - 2, steps + 2
+    return steps
+
+
+def cpu_baseline(wl, budget_steps: int) -> dict:
+    """Reference CPU implementation on a bounded sample, for the `cpu_baseline` object of our own line."""
+    from oracle.oracle import RefOracle, ref_available
+    from particle_simulator_b200.frame import DEVICE_CPU_THREAD_POOL
+
+    lx, ly = wl.grid_log2
+    if not ref_available(lx, ly):
+        return {"value": None, "unit": "particle-updates/s", "cores": 0, "kind": "reference",
+                "sample": f"oracle/_ref/libref_{lx}_{ly}.so not built"}
+    ref = RefOracle(lx, ly)
+    fb = wl.frame.copy()
+    fb.metadata["device"] = DEVICE_CPU_THREAD_POOL
+    fb.metadata["steps_per_frame"] = budget_steps
+    ref.prepare(fb)
+    executed = schedule_steps(budget_steps)
+    t = ref.run_frame()
+    return {"value": wl.particles * executed / t, "unit": "particle-updates/s", "cores": ref.hardware_threads,
+            "kind": "reference",
+            "sample": f"1 frame of {executed} leapfrog steps on the full {wl.particles}-particle scene, "
+                      f"Device::CpuThreadPool ({t:.1f} s)"}
+
+
+def run_ours(args, rank: int, world: int, local_rank: int) -> None:
+    import torch
+    import torch.distributed as dist
+
+    from particle_simulator_b200 import workloads
+    from particle_simulator_b200.frame import FrameBuffer, packet_size
+    from particle_simulator_b200.stepper import Stepper
+
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # the scene lives in page-locked host memory: it is what the e2e leg uploads every step
+    n_cap = 3162 * 3163
+    keep_in, store_in = pinned_storage(packet_size(n_cap))
+    keep_out, store_out = pinned_storage(packet_size(n_cap))
+    wl = workloads.config_10m_solid(storage=store_in)
+    wl.frame.metadata["steps_per_frame"] = STEPS_PER_FRAME
+    n = wl.particles
+    out = FrameBuffer(n, storage=store_out)
+    executed = schedule_steps(STEPS_PER_FRAME)
+
+    stream = torch.cuda.Stream()
+    st = Stepper(wl.grid_log2, n, device=local_rank)
+    st.set_stream(stream.cuda_stream)
+
+    # ---- device-resident leg -------------------------------------------------------------------
+    st.upload(wl.frame)
+    for _ in range(args.warmup):
+        st.run_frame_async()
+    st.sync()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    st.enable_step_timing(True)
+    launches0 = st.kernel_launches
+    steps0 = st.steps_executed
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record(stream)
+    for _ in range(args.steps):
+        st.run_frame_async()
+    e1.record(stream)
+    st.sync()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    clocks = sampler.stop()
+    step_ms, step_launches = st.step_timing()
+    st.enable_step_timing(False)
+    launches = st.kernel_launches - launches0
+    steps_done = st.steps_executed - steps0
+    assert steps_done == executed * args.steps
+    if world > 1:
+        t = torch.tensor([ms], device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    value = world * n * steps_done / (ms * 1e-3)
+
+    # ---- end-to-end leg: host frame in, host frame out, every step -------------------------------
+    for _ in range(min(args.warmup, 2)):
+        st.upload(wl.frame)
+        st.run_frame_async()
+        st.download(out)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        st.upload(wl.frame)
+        st.run_frame_async()
+        st.download(out)
+    torch.cuda.synchronize()
+    t_e2e = time.perf_counter() - t0
+    if world > 1:
+        t = torch.tensor([t_e2e], device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        t_e2e = float(t.item())
+    assert out.count == n
+    e2e_value = world * n * executed * args.steps / t_e2e
+
+    if rank == 0:
+        peak, peak_src = measured_hbm_peak()
+        kernel_ms = step_ms / max(step_launches, 1)
+        achieved = ALGO_BYTES_PER_UPDATE * n / (kernel_ms * 1e-3) / 1e9
+        line = {
+            "metric": "particle-updates/sec at 10M particles", "value": value, "unit": "particle-updates/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": wl.name, "description": wl.description, "particles": n,
+                       "steps_per_frame": STEPS_PER_FRAME, "leapfrog_steps_per_bench_step": executed,
+                       "rebins_per_bench_step": 6, "schedule": "reference (kernel_bucket.cuh:181-206)",
+                       "l2": "state (10M x 20 B x 2 buffers = 400 MB) is larger than the 126 MB L2; no flush",
+                       "replicas": world},
+            "roofline": {"bound": "hbm", "kernel": "step_kernel (fused 3x3-cell force + kick + drift)",
+                         "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "peak_source": peak_src, "traffic": recorded_traffic(),
+                         "algorithmic_bytes_per_launch": ALGO_BYTES_PER_UPDATE * n,
+                         "kernel_ms": kernel_ms, "kernel_launches_timed": step_launches,
+                         "kernel_share_of_step": step_ms / ms},
+            "e2e": {"value": e2e_value, "unit": "particle-updates/s", "h2d_bytes_per_step": packet_size(n),
+                    "d2h_bytes_per_step": packet_size(n), "ms_per_step": 1e3 * t_e2e / args.steps},
+            "gpu_launches": launches,
+            "clocks": clocks,
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            line["cpu_baseline"] = cpu_baseline(wl, args.cpu_steps)
+        print(json.dumps(line))
+    st.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main() -> None:
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
+    ap.add_argument("--ref-steps", type=int, default=2, help="--impl reference: steps_per_frame of one bench step")
+    ap.add_argument("--cpu-steps", type=int, default=3, help="cpu_baseline: steps_per_frame of the sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+    else:
+        run_ours(args, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

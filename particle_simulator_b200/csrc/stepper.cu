@@ -242,12 +242,12 @@ __device__ __forceinline__ void step_particle(uint32_t i, uint32_t cell, const u
         if (row < 0 || row >= (int)g.by) continue;
         int c0 = (row << g.lx) + (int)x0, c1 = (row << g.lx) + (int)x1;
         uint32_t s = cs[d][c0 - cs_lo[d]], e = cs[d][c1 + 1 - cs_lo[d]];
-        const uint2* base = pp[d] - pp_lo[d];
+        const uint2* win = pp[d] + (s - pp_lo[d]);  // window [s, e) of this row
         if (d == 1) {  // own row: skip j == i (kernel_bucket.cuh:85)
-            range_accumulate<FAST>(base + s, (int)(i - s), pi, a.ph, gx, gy);
-            range_accumulate<FAST>(base + i + 1, (int)(e - i - 1), pi, a.ph, gx, gy);
+            range_accumulate<FAST>(win, (int)(i - s), pi, a.ph, gx, gy);
+            range_accumulate<FAST>(win + (i + 1 - s), (int)(e - i - 1), pi, a.ph, gx, gy);
         } else {
-            range_accumulate<FAST>(base + s, (int)(e - s), pi, a.ph, gx, gy);
+            range_accumulate<FAST>(win, (int)(e - s), pi, a.ph, gx, gy);
         }
     }
     float2 f = field_force(pi, a.ph);
@@ -837,8 +837,9 @@ int psim_create(const PsimConfig* config, PsimStepper** out) {
     if (config->grid_x_log2 > 15 || config->grid_y_log2 > 15 || config->grid_x_log2 + config->grid_y_log2 > 28)
         return fail(s, PSIM_EINVAL, "psim_create: grid 2^%u x 2^%u is out of range", config->grid_x_log2,
                     config->grid_y_log2);
-    if (config->grid_x_log2 < 2 || config->grid_y_log2 < 2)
-        return fail(s, PSIM_EINVAL, "psim_create: the grid needs at least 4 cells per axis");
+    // separations inside the 3x3 stencil must fit a signed 32-bit fixed-point difference
+    if (config->grid_x_log2 < 3 || config->grid_y_log2 < 3)
+        return fail(s, PSIM_EINVAL, "psim_create: the grid needs at least 8 cells per axis");
     if (config->max_particles == 0 || config->max_particles > 0x7FFFFF00u)
         return fail(s, PSIM_EINVAL, "psim_create: max_particles out of range");
     if (config->schedule > PSIM_SCHEDULE_NATIVE) return fail(s, PSIM_EINVAL, "psim_create: unknown schedule");

@@ -81,9 +81,17 @@ class FrameBuffer:
     (particle_io/c_api/src/particle.rs:43-58).
     """
 
-    def __init__(self, capacity: int, metadata: np.ndarray | None = None):
+    def __init__(self, capacity: int, metadata: np.ndarray | None = None, storage: np.ndarray | None = None):
+        """`storage`: optional uint8 array of at least packet_size(capacity) bytes to build the frame
+        in (e.g. a view of page-locked memory); by default the frame owns ordinary host memory."""
         self.capacity = int(capacity)
-        self.raw = np.zeros(packet_size(self.capacity), dtype=np.uint8)
+        if storage is None:
+            self.raw = np.zeros(packet_size(self.capacity), dtype=np.uint8)
+        else:
+            if storage.dtype != np.uint8 or storage.size < packet_size(self.capacity) or storage.ctypes.data % 4:
+                raise ValueError("storage must be an aligned uint8 array of at least packet_size(capacity) bytes")
+            self.raw = storage[: packet_size(self.capacity)]
+            self.raw[: HEADER_DTYPE.itemsize] = 0
         self.header = self.raw[: HEADER_DTYPE.itemsize].view(HEADER_DTYPE)[0:1]
         self._all = self.raw[HEADER_DTYPE.itemsize :].view(PARTICLE_DTYPE)
         self.header["signature_start"] = np.frombuffer(SIGNATURE_START, dtype=np.uint8)
