@@ -16,7 +16,8 @@ Every fixture holds, for one seeded scene on the reference's fixed 64x64x16 grid
   frame_<S>      compacted result of Kernel::run_async with steps_per_frame = S from the fresh
                  binning (kernel_bucket.cuh:181-206), for each S in `frames`
   frame_steps    steps actually executed for each S (S=100 runs 101)
-  diag_*         double-precision energy / momentum diagnostics of those states (oracle_diagnostics)
+  diag_*         double-precision energy / momentum diagnostics of those states (oracle_diagnostics
+                 over the stencil pairs of a fresh binning of the state)
 """
 from __future__ import annotations
 
@@ -79,6 +80,12 @@ SCENES = {
 }
 
 
+def frame_of(particles: np.ndarray, meta: np.ndarray) -> FrameBuffer:
+    fb = FrameBuffer(max(len(particles), 1), np.asarray(meta).reshape(()))
+    fb.set_particles(particles)
+    return fb
+
+
 def counts_of(slots: np.ndarray, capacity: int) -> np.ndarray:
     return (slots["ty"].reshape(-1, capacity) >= 0).sum(axis=1).astype(np.uint32)
 
@@ -100,7 +107,13 @@ def main() -> None:
         }
 
         def diag(slots: np.ndarray, meta: np.ndarray) -> np.ndarray:
-            d = port.diagnostics(slots, meta)
+            # energies are taken over the stencil pairs of a FRESH binning of the state (64 slots per
+            # cell so nothing can be dropped): the pair set must not depend on how stale the
+            # membership of the state happens to be, or two equal states would show different PE
+            fresh = PortOracle(6, 6, 64)
+            fslots, dropped = fresh.prepare(frame_of(live(slots), meta))
+            assert dropped == 0
+            d = fresh.diagnostics(fslots, meta)
             return np.array([d["ke"], d["pe_pair"], d["pe_wall"], d["px"], d["py"], d["live"]])
 
         ref.prepare(fb)
