@@ -12,7 +12,8 @@
 //   vel[n]     float2 half-step velocities, updated in place by a step
 //   ty[n]      int32  species label, untouched by a step
 //   cell_start[cells+1] uint32 exclusive prefix sum of per-cell counts (CSR); cell = cx + cy*BX
-//   tile_first/tile_last[ceil(n/P)] first / last cell touched by each tile of P consecutive particles
+//   cell_id[n] uint32 cell of every particle as of the last binning (membership, not position)
+//   tiles[ceil(n/128)] TileDesc: what the CTA of each tile of 128 consecutive particles stages
 // Membership is by the LAST binning, exactly like the reference's slot array: between re-bins a
 // particle keeps its index and its cell even if it has drifted out of it (kernel_bucket.cuh:71-91).
 //
@@ -37,12 +38,14 @@ namespace {
 // ------------------------------------------------------------------------------------------------
 
 constexpr int kTile = 128;        // particles per CTA of the step kernel (= threads per CTA)
-constexpr int kCsCap = 288;       // cell_start entries staged per stencil row (cells spanned + 3)
-constexpr int kPosCap = 640;      // neighbour positions staged per stencil row
+constexpr int kCsCap = 288;       // cell_start entries staged per stencil row (multiple of 4)
+constexpr int kPosCap = 640;      // neighbour positions staged per stencil row (multiple of 2)
 constexpr int kScanItems = 8;     // cells per thread in the scan kernels
 constexpr int kScanThreads = 256;
 constexpr int kScanBlock = kScanItems * kScanThreads;
 constexpr uint32_t kNoKey = 0xFFFFFFFFu;
+constexpr int kPadCells = 8;      // readable slack after cell_start[cells] for 16-byte bulk copies
+constexpr int kPadParticles = 4;  // readable slack after pos[n] for 16-byte bulk copies
 
 struct Grid {
     uint32_t lx, ly;    // log2 cells in x / y
@@ -51,23 +54,51 @@ struct Grid {
     uint32_t sx, sy;    // 32 - lx, 32 - ly (shift that maps a fixed-point coordinate to its cell)
 };
 
+// How the non-integer part of the repulsive exponent is evaluated (see pair2 below).
+enum FracMode { kFracNone = 0, kFracPoly = 1, kFracEx2 = 2 };
+
 // Everything a step needs from FrameMetadata, pre-digested on the host once per metadata change
 // (the reference rebuilds ParticleParams, including a powf, in every thread of every step:
 // kernel_bucket.cuh:52, particle.cuh:53-55).
+//
+// Pair force in the units the kernel works in.  With q = sigma^2 / r^2:
+//   F_vec = C eps (m (s/r)^m - n (s/r)^n) / r^2 * r_vec                      (particle.cuh:63-66,97-103)
+//         = (C eps m / sigma^2) * (q^(m/2+1) - (n/m) q^(n/2+1)) * r_vec
+// r_vec is kept in raw fixed-point x units (dx, dy * yscale), so
+//   F_vec = pair_scale * sum_j g_j * (dx, dy')      with pair_scale = C eps m kx / sigma^2.
 struct Phys {
-    float ax, ay;        // (box / 2^32) / sigma : fixed-point units -> separation in units of sigma
-    float kx, ky;        // box / 2^32           : fixed-point units -> metres
-    float n, m;          // Mie exponents of species 0 (the only ones the reference uses)
-    float fn, fm;        // fractional parts of n/2 and m/2
-    int kn, km;          // integer parts of n/2 and m/2
-    float pair_scale;    // C * eps / sigma   : scaled pair sum -> newtons
+    float inv_c2;        // kx^2 / sigma^2: (raw x units)^2 -> r^2 / sigma^2
+    float yscale;        // ky / kx (1 for square cells): raw y units -> raw x units
+    float nm;            // n / m
+    float fn, fm;        // exponents n/2+1 = kn + fn, m/2+1 = km + fm  (|fn|, |fm| <= 0.5)
+    int kn, km;
+    float c1, c2, c3;    // 2^z ~ 1 + z (c1 + z (c2 + z c3)) on the z range of kFracPoly
+    float pair_scale;    // scaled pair sum -> newtons (x), see above
+    float pair_scale_y;  // same for y: pair_scale (dy' is already in x units)
     float wall_scale;    // C * eps * m
     float sigma;
-    float mass;
+    float inv_mass;
     float dt;
-    float box_w, box_h;
+    float kx, ky;        // box / 2^32: fixed-point units -> metres
+    float ux, uy;        // dt * 2^32 / box: velocity -> fixed-point displacement per step
     float cursor_x, cursor_y, cursor_r2;  // cursor_r2 = cursor_size^2 / 4
+    int wall_m6;         // m == 6: wall term by multiplication
+    float m;
 };
+
+// One tile of kTile consecutive particles: what its CTA stages in shared memory. Written at re-bin
+// time (tile_desc_kernel), read by every step until the next re-bin.  64 bytes.
+struct __align__(16) TileDesc {
+    uint32_t fits;       // 1: the three stencil rows fit the staging buffers
+    uint32_t first;      // first / last cell touched by the tile's own particles
+    uint32_t last;
+    uint32_t _pad;
+    uint32_t cs_lo[3];   // first cell_start entry staged per row (multiple of 4)
+    uint32_t cs_cnt[3];  // entries staged per row (multiple of 4; 0: row outside the grid)
+    uint32_t p_lo[3];    // first particle staged per row (even)
+    uint32_t p_cnt[3];   // particles staged per row (even)
+};
+static_assert(sizeof(TileDesc) == 64, "TileDesc is read as four 16-byte words");
 
 // ------------------------------------------------------------------------------------------------
 // Device helpers
@@ -89,71 +120,139 @@ __device__ __forceinline__ float fast_ex2(float x) {
     return r;
 }
 
-__device__ __forceinline__ float powi(float b, int k) {  // k is uniform across the grid
-    float r = 1.f;
+__device__ __forceinline__ float2 splat(float v) { return make_float2(v, v); }
+
+__device__ __forceinline__ float2 powi2(float2 b, int k) {  // k is uniform across the grid
+    float2 r = splat(1.f);
     while (k) {
-        if (k & 1) r *= b;
-        b *= b;
+        if (k & 1) r = __fmul2_rn(r, b);
+        b = __fmul2_rn(b, b);
         k >>= 1;
     }
     return r;
 }
 
 __device__ __forceinline__ uint32_t cell_of(uint2 p, const Grid& g) {
-    // kernel.cuh:224-226; a shift by 32 is undefined, so a 1-cell axis is handled explicitly
-    uint32_t cx = g.lx ? p.x >> g.sx : 0u;
-    uint32_t cy = g.ly ? p.y >> g.sy : 0u;
-    return cx + (cy << g.lx);
+    // kernel.cuh:224-226
+    return (p.x >> g.sx) + ((p.y >> g.sy) << g.lx);
 }
 
-// One pair: separation i -> j in units of sigma (f_dist, particle.cuh:41-47), Mie force
-// (particle.cuh:63-66,97-103) written on r^2 so that no square root is needed:
-//   F_vec = C eps (m (s/r)^m - n (s/r)^n) / r^2 * r_vec = (C eps / sigma) * (m q^(m/2) - n q^(n/2)) q * r'_vec
-// with r' = r / sigma and q = 1 / r'^2.  q^(n/2) = q^kn * 2^(fn * log2 q): the integer part by
-// multiplication, only the small fractional part through the approximate MUFU units, which keeps
-// the relative error of each term at a few 1e-7 (the fp32 evaluation in the reference, sigma/len
-// rounded and raised to the 14th power, is no better).
-template <bool FAST>
-__device__ __forceinline__ void pair_accumulate(uint2 pi, uint2 pj, const Phys& ph, float& gx, float& gy) {
-    float rx = __int2float_rn((int)(pj.x - pi.x)) * ph.ax;
-    float ry = __int2float_rn((int)(pj.y - pi.y)) * ph.ay;
-    float r2 = fmaf(ry, ry, rx * rx);
-    float q = fast_rcp(r2);
-    float l = fast_lg2(q);
-    float pm, pn;
-    if (FAST) {  // m = 6, floor(n/2) = 7 (the reference's default nitrogen parameters)
-        float q2 = q * q;
-        pm = q2 * q;
-        pn = (pm * pm) * q * fast_ex2(ph.fn * l);
-    } else {
-        pm = powi(q, ph.km);
-        if (ph.fm != 0.f) pm *= fast_ex2(ph.fm * l);
-        pn = powi(q, ph.kn);
-        if (ph.fn != 0.f) pn *= fast_ex2(ph.fn * l);
+// mbarrier + 1-D bulk copy (TMA) wrappers: global -> shared::cta, completion counted in bytes.
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_copy_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred P1;\n"
+        "LAB_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+        "@P1 bra DONE;\n"
+        "bra LAB_WAIT;\n"
+        "DONE:\n"
+        "}" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+
+// ------------------------------------------------------------------------------------------------
+// Two pairs at a time, on the packed fp32x2 pipe (FMUL2 / FFMA2, new on sm_100): the separation
+// i -> j (f_dist, particle.cuh:41-47: exact u32 difference, one int -> float conversion) and the Mie
+// force written on r^2 so that no square root is needed (see Phys).  With r2 = r^2 / sigma^2 and
+// q = 1 / r2, per pair   g = q^km - (n/m) q^kn * q^fn   (km = 4 for m = 6).
+// q^fn, the non-integer sliver of the repulsive exponent (n = 14.08 -> kn = 8, fn = 0.04), is
+// 2^(-fn log2 r2): MUFU.LG2, then either a host-fitted cubic in z = -fn log2 r2 (kFracPoly: |z| is
+// small, the cubic is exact to ~1e-8 where the term matters) or MUFU.EX2 (kFracEx2).  Integer powers
+// are products; each term keeps a relative error of a few 1e-7, no worse than the reference's own
+// fp32 `powf(sigma / len, n)`.  MUFU runs at 16 lanes/clk/SM (measured, tools/microbench.cu), so the
+// two MUFU ops per pair (RCP, LG2) are what bounds this loop, with issue slots a close second.
+// MASK1: the second pair of the packed couple does not exist (odd tail) and contributes exactly 0.
+// CLAMP: the window may contain i itself (own row): r2 is clamped away from 0 so that g stays
+// finite and the zero separation gives an exact 0 (kernel_bucket.cuh:85 skips j == i).
+// ------------------------------------------------------------------------------------------------
+template <int KN, int FRAC, bool ANISO, bool MASK1, bool CLAMP>
+__device__ __forceinline__ void pair2(uint2 pi, uint2 pj0, uint2 pj1, const Phys& ph, float2& gx, float2& gy) {
+    float2 x = make_float2(__int2float_rn((int)(pj0.x - pi.x)), __int2float_rn((int)(pj1.x - pi.x)));
+    float2 y = make_float2(__int2float_rn((int)(pj0.y - pi.y)), __int2float_rn((int)(pj1.y - pi.y)));
+    if (ANISO) y = __fmul2_rn(y, splat(ph.yscale));
+    float2 r2 = __ffma2_rn(y, y, __fmul2_rn(x, x));
+    r2 = __fmul2_rn(r2, splat(ph.inv_c2));
+    if (MASK1) r2.y = 1e12f;
+    if (CLAMP) {
+        r2.x = fmaxf(r2.x, 1e-2f);
+        r2.y = fmaxf(r2.y, 1e-2f);
     }
-    float g = fmaf(ph.m, pm, -ph.n * pn) * q;
-    gx = fmaf(g, rx, gx);
-    gy = fmaf(g, ry, gy);
+    float2 q = make_float2(fast_rcp(r2.x), fast_rcp(r2.y));
+    float2 q2 = __fmul2_rn(q, q);
+    float2 q4 = __fmul2_rn(q2, q2);
+    float2 pm, pn;
+    if (KN > 0) {  // m = 6 (q^4) and a compile-time integer part of n/2 + 1
+        pm = q4;
+        if (KN == 5) pn = __fmul2_rn(q4, q);
+        else if (KN == 6) pn = __fmul2_rn(q4, q2);
+        else if (KN == 7) pn = __fmul2_rn(__fmul2_rn(q4, q2), q);
+        else if (KN == 8) pn = __fmul2_rn(q4, q4);
+        else if (KN == 9) pn = __fmul2_rn(__fmul2_rn(q4, q4), q);
+        else pn = __fmul2_rn(__fmul2_rn(q4, q4), q2);
+    } else {  // any exponents: run-time integer parts
+        pm = powi2(q, ph.km);
+        pn = powi2(q, ph.kn);
+    }
+    if (FRAC != kFracNone) {
+        float2 l = make_float2(fast_lg2(r2.x), fast_lg2(r2.y));
+        float2 z = __fmul2_rn(l, splat(-ph.fn));
+        float2 e;
+        if (FRAC == kFracPoly) {
+            e = __ffma2_rn(z, splat(ph.c3), splat(ph.c2));
+            e = __ffma2_rn(z, e, splat(ph.c1));
+            e = __ffma2_rn(z, e, splat(1.f));
+        } else {
+            e = make_float2(fast_ex2(z.x), fast_ex2(z.y));
+        }
+        pn = __fmul2_rn(pn, e);
+        if (KN == 0 && ph.fm != 0.f) {
+            float2 zm = __fmul2_rn(l, splat(-ph.fm));
+            pm = __fmul2_rn(pm, make_float2(fast_ex2(zm.x), fast_ex2(zm.y)));
+        }
+    }
+    float2 g = __ffma2_rn(pn, splat(-ph.nm), pm);
+    gx = __ffma2_rn(g, x, gx);
+    gy = __ffma2_rn(g, y, gy);
 }
 
-template <bool FAST>
-__device__ __forceinline__ void range_accumulate(const uint2* __restrict__ pj, int count, uint2 pi, const Phys& ph,
-                                                 float& gx, float& gy) {
-#pragma unroll 4
-    for (int k = 0; k < count; ++k) pair_accumulate<FAST>(pi, pj[k], ph, gx, gy);
+// All of one window [0, count) of staged neighbours, two at a time, in ascending index order.
+template <int KN, int FRAC, bool ANISO, bool CLAMP>
+__device__ __forceinline__ void window_accumulate(const uint2* __restrict__ pj, int count, uint2 pi, const Phys& ph,
+                                                  float2& gx, float2& gy) {
+    int k = 0;
+#pragma unroll 2
+    for (; k + 1 < count; k += 2) pair2<KN, FRAC, ANISO, false, CLAMP>(pi, pj[k], pj[k + 1], ph, gx, gy);
+    if (k < count) pair2<KN, FRAC, ANISO, true, CLAMP>(pi, pj[k], pi, ph, gx, gy);
 }
 
 // Repulsive wall term C eps m (sigma/d)^m / d (particle.cuh:68-71).
 __device__ __forceinline__ float wall_term(float d, const Phys& ph) {
-    float q = ph.sigma / d;
+    float inv_d = fast_rcp(d);
+    float q = ph.sigma * inv_d;
     float pw;
-    if (ph.km == 3 && ph.fm == 0.f) {
+    if (ph.wall_m6) {
         float q2 = q * q;
         pw = q2 * q2 * q2;
     } else {
         pw = fast_ex2(ph.m * fast_lg2(q));
     }
-    return ph.wall_scale * pw / d;
+    return ph.wall_scale * pw * inv_d;
 }
 
 // Cursor + wall forces on one particle (kernel_bucket.cuh:54-69, particle.cuh:125-144).
@@ -164,7 +263,7 @@ __device__ __forceinline__ float2 field_force(uint2 p, const Phys& ph) {
     float dy = ph.cursor_y - __uint2float_rn(p.y) * inv32;
     float sq = dx * dx + dy * dy;
     if (sq < ph.cursor_r2) {
-        float c = 8e-12f / (sq + 1.f);
+        float c = 8e-12f * fast_rcp(sq + 1.f);
         f.x = dx > 0 ? -c : c;
         f.y = dy > 0 ? -c : c;
     }
@@ -176,17 +275,14 @@ __device__ __forceinline__ float2 field_force(uint2 p, const Phys& ph) {
 }
 
 // Leapfrog kick + drift on half-step velocities with wrapping fixed-point positions
-// (f_apply_force, particle.cuh:105-123). Per particle, so the exact divisions are kept.
+// (f_apply_force, particle.cuh:105-123): v += F/m dt; x += round(v dt / box * 2^32) (wrapping).
+// The reference's divisions by the constants mass and box are multiplications by their
+// reciprocals here (a 1-ulp difference, far inside the 1e-5 tolerance).
 __device__ __forceinline__ void integrate(uint2 p, float2 v, float2 f, const Phys& ph, uint2& p_out, float2& v_out) {
-    const float two32 = 4294967296.f;
-    float axl = f.x / ph.mass;
-    float ayl = f.y / ph.mass;
-    v_out.x = v.x + axl * ph.dt;
-    v_out.y = v.y + ayl * ph.dt;
-    float dx = v_out.x * ph.dt;
-    float dy = v_out.y * ph.dt;
-    p_out.x = p.x + (uint32_t)(long long)roundf((dx / ph.box_w) * two32);
-    p_out.y = p.y + (uint32_t)(long long)roundf((dy / ph.box_h) * two32);
+    v_out.x = fmaf(f.x * ph.inv_mass, ph.dt, v.x);
+    v_out.y = fmaf(f.y * ph.inv_mass, ph.dt, v.y);
+    p_out.x = p.x + (uint32_t)(long long)roundf(v_out.x * ph.ux);
+    p_out.y = p.y + (uint32_t)(long long)roundf(v_out.y * ph.uy);
 }
 
 // largest c in [0, count) with a[c] <= i, given a[0] <= i  (a is non-decreasing)
@@ -205,54 +301,49 @@ __device__ __forceinline__ int last_le(const uint32_t* a, int count, uint32_t i)
 //
 // CTA b owns particles [b*kTile, (b+1)*kTile). Because the arrays are cell-sorted and cells are
 // row-major, everything those particles interact with lies in three contiguous index ranges, one
-// per stencil row: cells [first-1, last+1] shifted by -BX, 0, +BX. The CTA stages the cell_start
-// entries and the positions of those three ranges in shared memory once, then every thread walks
-// its own three windows (cells cx-1..cx+1 of rows cy-1..cy+1, clipped at the grid edge exactly like
-// kernel_bucket.cuh:74-77) in ascending index order -- the same (row, column, slot) order in which
-// the reference accumulates, so the fp32 sum is formed in the same sequence.
-// Tiles whose stencil does not fit the staging buffers (very sparse or very clustered spots) take
-// the same code path with the pointers aimed at global memory instead.
+// per stencil row: cells [first-1, last+1] shifted by -BX, 0, +BX. One thread reads the tile's
+// descriptor and issues up to six 1-D bulk copies (TMA, cp.async.bulk -> mbarrier) that stage the
+// cell_start entries and the positions of those ranges in shared memory; meanwhile every thread
+// loads its own particle.  Then every thread walks its own three windows (cells cx-1..cx+1 of rows
+// cy-1..cy+1, clipped at the grid edge exactly like kernel_bucket.cuh:74-77) in ascending index
+// order, the (row, column, slot) order of the reference's loop.
+// Tiles whose stencil does not fit the staging buffers (very sparse or very clustered spots) run
+// the same code with the pointers aimed at global memory instead.
 // ------------------------------------------------------------------------------------------------
 
 struct StepArgs {
     const uint2* __restrict__ pos_in;
     uint2* __restrict__ pos_out;
     float2* __restrict__ vel;
+    const uint32_t* __restrict__ cell_id;
     const uint32_t* __restrict__ cell_start;
-    const uint32_t* __restrict__ tile_first;
-    const uint32_t* __restrict__ tile_last;
+    const TileDesc* __restrict__ tiles;
     uint32_t n;
     Grid g;
     Phys ph;
 };
 
-template <bool FAST>
-__device__ __forceinline__ void step_particle(uint32_t i, uint32_t cell, const uint32_t* const cs[3],
-                                              const int cs_lo[3], const uint2* const pp[3], const uint32_t pp_lo[3],
-                                              const StepArgs& a) {
+template <int KN, int FRAC, bool ANISO>
+__device__ __forceinline__ void step_particle(uint32_t i, uint2 pi, float2 vi, uint32_t cell,
+                                              const uint32_t* const cs[3], const uint32_t cs_lo[3],
+                                              const uint2* const pp[3], const uint32_t pp_lo[3], const StepArgs& a) {
     const Grid& g = a.g;
-    uint2 pi = a.pos_in[i];
-    float2 vi = a.vel[i];
     uint32_t cx = cell & (g.bx - 1), cy = cell >> g.lx;
     uint32_t x0 = cx == 0 ? 0 : cx - 1, x1 = cx == g.bx - 1 ? cx : cx + 1;
-    float gx = 0.f, gy = 0.f;
+    float2 gx = splat(0.f), gy = splat(0.f);
 #pragma unroll
     for (int d = 0; d < 3; ++d) {
         int row = (int)cy + d - 1;
         if (row < 0 || row >= (int)g.by) continue;
-        int c0 = (row << g.lx) + (int)x0, c1 = (row << g.lx) + (int)x1;
+        uint32_t c0 = ((uint32_t)row << g.lx) + x0, c1 = ((uint32_t)row << g.lx) + x1;
         uint32_t s = cs[d][c0 - cs_lo[d]], e = cs[d][c1 + 1 - cs_lo[d]];
         const uint2* win = pp[d] + (s - pp_lo[d]);  // window [s, e) of this row
-        if (d == 1) {  // own row: skip j == i (kernel_bucket.cuh:85)
-            range_accumulate<FAST>(win, (int)(i - s), pi, a.ph, gx, gy);
-            range_accumulate<FAST>(win + (i + 1 - s), (int)(e - i - 1), pi, a.ph, gx, gy);
-        } else {
-            range_accumulate<FAST>(win, (int)(e - s), pi, a.ph, gx, gy);
-        }
+        if (d == 1) window_accumulate<KN, FRAC, ANISO, true>(win, (int)(e - s), pi, a.ph, gx, gy);  // contains i
+        else window_accumulate<KN, FRAC, ANISO, false>(win, (int)(e - s), pi, a.ph, gx, gy);
     }
     float2 f = field_force(pi, a.ph);
-    f.x = fmaf(a.ph.pair_scale, gx, f.x);
-    f.y = fmaf(a.ph.pair_scale, gy, f.y);
+    f.x = fmaf(a.ph.pair_scale, gx.x + gx.y, f.x);
+    f.y = fmaf(a.ph.pair_scale_y, gy.x + gy.y, f.y);
     uint2 po;
     float2 vo;
     integrate(pi, vi, f, a.ph, po, vo);
@@ -260,74 +351,52 @@ __device__ __forceinline__ void step_particle(uint32_t i, uint32_t cell, const u
     a.vel[i] = vo;
 }
 
-template <bool FAST>
-__global__ void __launch_bounds__(kTile) step_kernel(const StepArgs a) {
-    __shared__ uint32_t s_cs[3][kCsCap];
-    __shared__ uint2 s_pos[3][kPosCap];
-    __shared__ int s_fits;
+template <int KN, int FRAC, bool ANISO>
+__global__ void __launch_bounds__(kTile, 8) step_kernel(const StepArgs a) {
+    __shared__ __align__(16) uint32_t s_cs[3][kCsCap];
+    __shared__ __align__(16) uint2 s_pos[3][kPosCap];
+    __shared__ __align__(8) uint64_t s_bar;
 
-    const Grid& g = a.g;
     const uint32_t b = blockIdx.x;
     const uint32_t i = b * kTile + threadIdx.x;
-    const int first = (int)a.tile_first[b], last = (int)a.tile_last[b];
+    const TileDesc t = a.tiles[b];
 
-    // linear cell range of each stencil row, clipped to the grid
-    int lo[3], hi[3];
+    if (t.fits) {
+        if (threadIdx.x == 0) {
+            mbar_init(&s_bar, 1);
+            uint32_t bytes = 0;
 #pragma unroll
-    for (int d = 0; d < 3; ++d) {
-        int shift = (d - 1) * (int)g.bx;
-        lo[d] = max(first - 1 + shift, 0);
-        hi[d] = min(last + 1 + shift, (int)g.cells - 1);
-    }
-    const bool cs_fits = last - first + 4 <= kCsCap;
-    if (threadIdx.x == 0) s_fits = cs_fits ? 1 : 0;
-    if (cs_fits) {
+            for (int d = 0; d < 3; ++d) bytes += t.cs_cnt[d] * 4u + t.p_cnt[d] * 8u;
+            mbar_arrive_expect_tx(&s_bar, bytes);
 #pragma unroll
-        for (int d = 0; d < 3; ++d) {
-            int cnt = hi[d] - lo[d] + 2;  // entries lo..hi+1 (may be <= 0 for a clipped-away row)
-            for (int k = threadIdx.x; k < cnt; k += kTile) s_cs[d][k] = a.cell_start[lo[d] + k];
-        }
-    }
-    __syncthreads();
-    uint32_t plo[3] = {0, 0, 0};
-    if (cs_fits) {
-        bool fits = true;
-        uint32_t pcnt[3];
-#pragma unroll
-        for (int d = 0; d < 3; ++d) {
-            if (hi[d] >= lo[d]) {
-                plo[d] = s_cs[d][0];
-                pcnt[d] = s_cs[d][hi[d] - lo[d] + 1] - plo[d];
-            } else {
-                pcnt[d] = 0;
+            for (int d = 0; d < 3; ++d) {
+                if (t.cs_cnt[d]) bulk_copy_g2s(s_cs[d], a.cell_start + t.cs_lo[d], t.cs_cnt[d] * 4u, &s_bar);
+                if (t.p_cnt[d]) bulk_copy_g2s(s_pos[d], a.pos_in + t.p_lo[d], t.p_cnt[d] * 8u, &s_bar);
             }
-            fits = fits && pcnt[d] <= (uint32_t)kPosCap;
         }
-        if (fits) {
-#pragma unroll
-            for (int d = 0; d < 3; ++d)
-                for (uint32_t k = threadIdx.x; k < pcnt[d]; k += kTile) s_pos[d][k] = a.pos_in[plo[d] + k];
-        } else if (threadIdx.x == 0) {
-            s_fits = 0;  // every thread computes the same `fits`; one writer is enough
-        }
+        __syncthreads();  // the barrier is initialised before anyone polls it
     }
-    __syncthreads();
-    if (i >= a.n) return;
-
-    if (s_fits) {
+    const bool live = i < a.n;
+    uint2 pi = make_uint2(0, 0);
+    float2 vi = make_float2(0.f, 0.f);
+    uint32_t cell = 0;
+    if (live) {
+        pi = a.pos_in[i];
+        vi = a.vel[i];
+        cell = a.cell_id[i];
+    }
+    if (t.fits) {
+        mbar_wait(&s_bar, 0);
+        if (!live) return;
         const uint32_t* cs[3] = {s_cs[0], s_cs[1], s_cs[2]};
         const uint2* pp[3] = {s_pos[0], s_pos[1], s_pos[2]};
-        // own cell: the cell c in [first, last] with cell_start[c] <= i < cell_start[c+1]
-        int off = first - lo[1];
-        uint32_t cell = (uint32_t)(first + last_le(s_cs[1] + off, last - first + 1, i));
-        step_particle<FAST>(i, cell, cs, lo, pp, plo, a);
+        step_particle<KN, FRAC, ANISO>(i, pi, vi, cell, cs, t.cs_lo, pp, t.p_lo, a);
     } else {
+        if (!live) return;
         const uint32_t* cs[3] = {a.cell_start, a.cell_start, a.cell_start};
         const uint2* pp[3] = {a.pos_in, a.pos_in, a.pos_in};
-        const int zero[3] = {0, 0, 0};
-        const uint32_t uzero[3] = {0, 0, 0};
-        uint32_t cell = (uint32_t)(first + last_le(a.cell_start + first, last - first + 1, i));
-        step_particle<FAST>(i, cell, cs, zero, pp, uzero, a);
+        const uint32_t zero[3] = {0, 0, 0};
+        step_particle<KN, FRAC, ANISO>(i, pi, vi, cell, cs, zero, pp, zero, a);
     }
 }
 
@@ -464,7 +533,8 @@ __global__ void scatter_kernel(Source src, uint32_t count, Grid g, const uint32_
 template <bool AOS>
 __global__ void gather_kernel(Source src, uint32_t live, Grid g, const uint32_t* __restrict__ cell_start,
                               const uint32_t* __restrict__ perm, uint2* __restrict__ pos_out,
-                              float2* __restrict__ vel_out, int32_t* __restrict__ ty_out) {
+                              float2* __restrict__ vel_out, int32_t* __restrict__ ty_out,
+                              uint32_t* __restrict__ cell_id_out) {
     uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= live) return;
     uint32_t i = perm[p];
@@ -489,17 +559,43 @@ __global__ void gather_kernel(Source src, uint32_t live, Grid g, const uint32_t*
     pos_out[dst] = pos;
     vel_out[dst] = vel;
     ty_out[dst] = ty;
+    cell_id_out[dst] = key;
 }
 
-// first / last cell of every tile of kTile consecutive particles
-__global__ void tile_cells_kernel(const uint32_t* __restrict__ cell_start, uint32_t cells, uint32_t n,
-                                  uint32_t* __restrict__ tile_first, uint32_t* __restrict__ tile_last) {
+// One descriptor per tile of kTile consecutive particles: the cell range of the tile, and for each of
+// the three stencil rows the (16-byte aligned) slices of cell_start and of the position array that its
+// CTA stages in shared memory (see step_kernel).
+__global__ void tile_desc_kernel(const uint32_t* __restrict__ cell_start, Grid g, uint32_t n,
+                                 TileDesc* __restrict__ tiles) {
     uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
-    uint32_t tiles = (n + kTile - 1) / kTile;
-    if (b >= tiles) return;
+    uint32_t ntiles = (n + kTile - 1) / kTile;
+    if (b >= ntiles) return;
     uint32_t i0 = b * kTile, i1 = min(n, i0 + kTile) - 1;
-    tile_first[b] = (uint32_t)last_le(cell_start, (int)cells, i0);
-    tile_last[b] = (uint32_t)last_le(cell_start, (int)cells, i1);
+    TileDesc t;
+    t.first = (uint32_t)last_le(cell_start, (int)g.cells, i0);
+    t.last = (uint32_t)last_le(cell_start, (int)g.cells, i1);
+    t._pad = 0;
+    bool fits = true;
+    for (int d = 0; d < 3; ++d) {
+        long long shift = (long long)(d - 1) * (long long)g.bx;
+        long long lo = max((long long)t.first - 1 + shift, 0ll);
+        long long hi = min((long long)t.last + 1 + shift, (long long)g.cells - 1);
+        if (hi < lo) {  // the whole row lies outside the grid
+            t.cs_lo[d] = t.cs_cnt[d] = t.p_lo[d] = t.p_cnt[d] = 0;
+            continue;
+        }
+        uint32_t cs_lo = (uint32_t)lo & ~3u;
+        uint32_t cs_cnt = (((uint32_t)hi + 2 - cs_lo) + 3u) & ~3u;  // entries lo .. hi+1
+        uint32_t p_lo = cell_start[lo] & ~1u;
+        uint32_t p_cnt = ((cell_start[hi + 1] - p_lo) + 1u) & ~1u;
+        t.cs_lo[d] = cs_lo;
+        t.cs_cnt[d] = cs_cnt;
+        t.p_lo[d] = p_lo;
+        t.p_cnt[d] = p_cnt;
+        fits = fits && cs_cnt <= (uint32_t)kCsCap && p_cnt <= (uint32_t)kPosCap;
+    }
+    t.fits = fits ? 1u : 0u;
+    tiles[b] = t;
 }
 
 // snapshot: pack the structure of arrays back into wire-format records (particle.rs:10-18)
@@ -528,7 +624,9 @@ struct PsimStepper {
     PsimConfig cfg{};
     Grid grid{};
     Phys phys{};
-    bool fast_path = false;
+    int kernel_kn = 0;         // step-kernel variant: integer part of n/2+1 (0: run-time exponents)
+    int kernel_frac = kFracEx2;
+    bool kernel_aniso = false;
     FrameMetadata meta{};
     int device = 0;
 
@@ -548,8 +646,8 @@ struct PsimStepper {
     uint32_t* block_sum = nullptr;
     uint32_t* rank = nullptr;
     uint32_t* perm = nullptr;
-    uint32_t* tile_first = nullptr;
-    uint32_t* tile_last = nullptr;
+    uint32_t* cell_id = nullptr;  // n: cell of every particle as of the last binning
+    TileDesc* tiles = nullptr;    // ceil(n / kTile)
     Particle* staging = nullptr;  // ingest (AoS) and snapshot (AoS) buffer
     uint32_t* h_total = nullptr;  // pinned
 
@@ -594,39 +692,157 @@ int fail(PsimStepper* s, int code, const char* fmt, ...) {
                         __LINE__);                                                                        \
     } while (0)
 
-Phys make_phys(const FrameMetadata& m) {
+// Cubic for 2^z on z in [z_lo, z_hi] (weighted least squares on Chebyshev nodes; the constant term is
+// pinned to 1 so that z = 0 is exact). Returns the largest error of (n/m) q^(kn+fn) it causes, i.e. the
+// absolute error of g, over the q range that maps onto [z_lo, z_hi].
+double fit_exp2_cubic(double fn, double kn, double nm, double q_lo, double q_hi, float c[3]) {
+    const int N = 256;
+    const double ln2 = 0.69314718055994530942;
+    // normal equations for e(z) - 1 = z (c1 + c2 z + c3 z^2), weight w = how much an error costs in g
+    double A[3][3] = {{0}}, B[3] = {0};
+    auto weight = [&](double q) { return std::min(nm * std::pow(q, kn + fn), 0.15) + 1e-6; };
+    for (int k = 0; k < N; ++k) {
+        double t = std::cos(3.14159265358979323846 * (k + 0.5) / N);
+        double lq = 0.5 * (std::log2(q_hi) + std::log2(q_lo)) + 0.5 * (std::log2(q_hi) - std::log2(q_lo)) * t;
+        double q = std::exp2(lq), z = fn * lq, w = weight(q);
+        double basis[3] = {z, z * z, z * z * z}, rhs = std::exp(z * ln2) - 1.0;
+        for (int r = 0; r < 3; ++r) {
+            for (int cc = 0; cc < 3; ++cc) A[r][cc] += w * w * basis[r] * basis[cc];
+            B[r] += w * w * basis[r] * rhs;
+        }
+    }
+    // 3x3 solve (Gaussian elimination with partial pivoting)
+    int idx[3] = {0, 1, 2};
+    double M[3][4];
+    for (int r = 0; r < 3; ++r) {
+        for (int cc = 0; cc < 3; ++cc) M[r][cc] = A[r][cc];
+        M[r][3] = B[r];
+    }
+    for (int col = 0; col < 3; ++col) {
+        int piv = col;
+        for (int r = col + 1; r < 3; ++r)
+            if (std::fabs(M[r][col]) > std::fabs(M[piv][col])) piv = r;
+        std::swap(idx[col], idx[piv]);
+        for (int cc = 0; cc < 4; ++cc) std::swap(M[col][cc], M[piv][cc]);
+        if (M[col][col] == 0.0) {  // fn == 0 or a degenerate range: Taylor coefficients
+            c[0] = (float)ln2;
+            c[1] = (float)(ln2 * ln2 / 2);
+            c[2] = (float)(ln2 * ln2 * ln2 / 6);
+            return fn == 0.0 ? 0.0 : 1.0;
+        }
+        for (int r = 0; r < 3; ++r) {
+            if (r == col) continue;
+            double f = M[r][col] / M[col][col];
+            for (int cc = col; cc < 4; ++cc) M[r][cc] -= f * M[col][cc];
+        }
+    }
+    for (int r = 0; r < 3; ++r) c[r] = (float)(M[r][3] / M[r][r]);
+    double worst = 0;
+    for (int k = 0; k <= 4 * N; ++k) {
+        double lq = std::log2(q_lo) + (std::log2(q_hi) - std::log2(q_lo)) * k / (4.0 * N);
+        double q = std::exp2(lq), z = fn * lq;
+        double approx = 1.0 + z * ((double)c[0] + z * ((double)c[1] + z * (double)c[2]));
+        double err = std::fabs(approx - std::exp(z * ln2));
+        // absolute error of g, and -- where the repulsive term dominates -- relative to the term itself
+        double cost = std::min(nm * std::pow(q, kn + fn) * err, err / 2e-7 * 3e-8);
+        worst = std::max(worst, cost);
+    }
+    return worst;
+}
+
+Phys make_phys(const FrameMetadata& m, int* kernel_kn, int* kernel_frac, bool* aniso) {
     const MiePotentialParams& p = m.particles[0];  // kernel_bucket.cuh:52
     Phys ph{};
     const float two32 = 4294967296.f;
     ph.kx = m.box_width / two32;
     ph.ky = m.box_height / two32;
-    ph.ax = ph.kx / p.sigma;
-    ph.ay = ph.ky / p.sigma;
-    ph.n = p.n;
+    ph.yscale = ph.ky / ph.kx;
+    *aniso = ph.yscale != 1.f;
+    ph.inv_c2 = (ph.kx / p.sigma) * (ph.kx / p.sigma);
+    ph.nm = p.n / p.m;
+    // exponents of q = sigma^2 / r^2: m/2 + 1 and n/2 + 1, split into the nearest integer and a rest
+    float em = p.m / 2.f + 1.f, en = p.n / 2.f + 1.f;
+    ph.km = (int)lrintf(em);
+    ph.kn = (int)lrintf(en);
+    ph.fm = em - (float)ph.km;
+    ph.fn = en - (float)ph.kn;
     ph.m = p.m;
-    float hn = p.n / 2.f, hm = p.m / 2.f;
-    ph.kn = (int)floorf(hn);
-    ph.km = (int)floorf(hm);
-    ph.fn = hn - (float)ph.kn;
-    ph.fm = hm - (float)ph.km;
     float C = (p.n / (p.n - p.m)) * powf(p.n / p.m, p.m / (p.n - p.m));  // particle.cuh:53-55
-    ph.pair_scale = C * p.epsilon / p.sigma;
+    ph.pair_scale = C * p.epsilon * p.m * ph.kx / (p.sigma * p.sigma);
+    ph.pair_scale_y = ph.pair_scale;
     ph.wall_scale = C * p.epsilon * p.m;
+    ph.wall_m6 = p.m == 6.f;
     ph.sigma = p.sigma;
-    ph.mass = (float)6.63352599e-26;  // particle.cuh:51
+    ph.inv_mass = 1.f / (float)6.63352599e-26;  // particle.cuh:51
     ph.dt = m.step_dt;
-    ph.box_w = m.box_width;
-    ph.box_h = m.box_height;
+    ph.ux = m.step_dt / m.box_width * two32;
+    ph.uy = m.step_dt / m.box_height * two32;
     ph.cursor_x = m.cursor_pos[0];
     ph.cursor_y = m.cursor_pos[1];
     ph.cursor_r2 = m.cursor_size * m.cursor_size / 4;
+
+    // Which step-kernel variant evaluates these exponents.
+    //   m = 6 and 5 <= kn <= 10: the integer powers are compile-time products (KN = kn);
+    //   the rest fn of the repulsive exponent: none / cubic in z / MUFU.EX2, see pair2().
+    // The cubic is accepted only if the error it adds to g stays below 3e-8 (g is O(0.1..1); fp32
+    // rounding of the terms themselves is ~1e-7) over r from 0.5 sigma to beyond the stencil reach.
+    ph.c1 = 0.69314718f;
+    ph.c2 = 0.24022651f;
+    ph.c3 = 0.05550411f;
+    bool fixed_powers = ph.km == 4 && ph.fm == 0.f && ph.kn >= 5 && ph.kn <= 10;
+    *kernel_kn = fixed_powers ? ph.kn : 0;
+    if (ph.fn == 0.f && (fixed_powers || ph.fm == 0.f)) {
+        *kernel_frac = kFracNone;
+    } else if (fixed_powers) {
+        float c[3];
+        double cost = fit_exp2_cubic(ph.fn, ph.kn, ph.nm, 1e-3, 4.0, c);
+        if (cost <= 3e-8) {
+            ph.c1 = c[0];
+            ph.c2 = c[1];
+            ph.c3 = c[2];
+            *kernel_frac = kFracPoly;
+        } else {
+            *kernel_frac = kFracEx2;
+        }
+    } else {
+        *kernel_frac = kFracEx2;
+    }
     return ph;
 }
 
 void apply_metadata(PsimStepper* s, const FrameMetadata& m) {
     s->meta = m;
-    s->phys = make_phys(m);
-    s->fast_path = s->phys.km == 3 && s->phys.fm == 0.f && s->phys.kn == 7 && s->phys.kn >= 0;
+    s->phys = make_phys(m, &s->kernel_kn, &s->kernel_frac, &s->kernel_aniso);
+}
+
+template <int KN, int FRAC>
+void launch_step_aniso(PsimStepper* s, const StepArgs& a, uint32_t tiles) {
+    if (s->kernel_aniso) step_kernel<KN, FRAC, true><<<tiles, kTile, 0, s->stream>>>(a);
+    else step_kernel<KN, FRAC, false><<<tiles, kTile, 0, s->stream>>>(a);
+}
+
+template <int KN>
+void launch_step_frac(PsimStepper* s, const StepArgs& a, uint32_t tiles) {
+    switch (s->kernel_frac) {
+        case kFracNone: launch_step_aniso<KN, kFracNone>(s, a, tiles); break;
+        case kFracPoly: launch_step_aniso<KN, kFracPoly>(s, a, tiles); break;
+        default: launch_step_aniso<KN, kFracEx2>(s, a, tiles); break;
+    }
+}
+
+void launch_step(PsimStepper* s, const StepArgs& a, uint32_t tiles) {
+    switch (s->kernel_kn) {
+        case 5: launch_step_frac<5>(s, a, tiles); break;
+        case 6: launch_step_frac<6>(s, a, tiles); break;
+        case 7: launch_step_frac<7>(s, a, tiles); break;
+        case 8: launch_step_frac<8>(s, a, tiles); break;
+        case 9: launch_step_frac<9>(s, a, tiles); break;
+        case 10: launch_step_frac<10>(s, a, tiles); break;
+        default:  // run-time exponents; kFracPoly is never selected for them
+            if (s->kernel_frac == kFracNone) launch_step_aniso<0, kFracNone>(s, a, tiles);
+            else launch_step_aniso<0, kFracEx2>(s, a, tiles);
+            break;
+    }
 }
 
 inline uint32_t div_up(uint32_t a, uint32_t b) { return (a + b - 1) / b; }
@@ -646,8 +862,7 @@ int enqueue_scan(PsimStepper* s) {
 int enqueue_tiles(PsimStepper* s) {
     uint32_t tiles = div_up(s->n, kTile);
     if (tiles == 0) return PSIM_OK;
-    tile_cells_kernel<<<div_up(tiles, 128), 128, 0, s->stream>>>(s->cell_start, s->grid.cells, s->n, s->tile_first,
-                                                                 s->tile_last);
+    tile_desc_kernel<<<div_up(tiles, 128), 128, 0, s->stream>>>(s->cell_start, s->grid, s->n, s->tiles);
     s->launches += 1;
     CK(cudaGetLastError());
     return PSIM_OK;
@@ -666,7 +881,7 @@ int enqueue_rebin(PsimStepper* s) {
     scatter_kernel<false><<<div_up(n, tb), tb, 0, s->stream>>>(src, n, s->grid, s->cell_start, s->rank, s->perm);
     gather_kernel<false><<<div_up(n, tb), tb, 0, s->stream>>>(src, n, s->grid, s->cell_start, s->perm,
                                                               s->pos[s->cur_pos ^ 1], s->vel[s->cur_vel ^ 1],
-                                                              s->ty[s->cur_ty ^ 1]);
+                                                              s->ty[s->cur_ty ^ 1], s->cell_id);
     s->launches += 2;
     CK(cudaGetLastError());
     s->cur_pos ^= 1;
@@ -687,9 +902,9 @@ int enqueue_step(PsimStepper* s) {
     a.pos_in = s->pos[s->cur_pos];
     a.pos_out = s->pos[s->cur_pos ^ 1];
     a.vel = s->vel[s->cur_vel];
+    a.cell_id = s->cell_id;
     a.cell_start = s->cell_start;
-    a.tile_first = s->tile_first;
-    a.tile_last = s->tile_last;
+    a.tiles = s->tiles;
     a.n = s->n;
     a.g = s->grid;
     a.ph = s->phys;
@@ -707,8 +922,7 @@ int enqueue_step(PsimStepper* s) {
         s->timing_used += 1;
         CK(cudaEventRecord(e0, s->stream));
     }
-    if (s->fast_path) step_kernel<true><<<tiles, kTile, 0, s->stream>>>(a);
-    else step_kernel<false><<<tiles, kTile, 0, s->stream>>>(a);
+    launch_step(s, a, tiles);
     if (s->timing) CK(cudaEventRecord(e1, s->stream));
     CK(cudaGetLastError());
     s->launches += 1;
@@ -767,7 +981,7 @@ int ingest_staged(PsimStepper* s, uint32_t count) {
         scatter_kernel<true><<<div_up(count, tb), tb, 0, s->stream>>>(src, count, s->grid, s->cell_start, s->rank,
                                                                       s->perm);
         gather_kernel<true><<<div_up(live, tb), tb, 0, s->stream>>>(src, live, s->grid, s->cell_start, s->perm,
-                                                                    s->pos[0], s->vel[0], s->ty[0]);
+                                                                    s->pos[0], s->vel[0], s->ty[0], s->cell_id);
         s->launches += 2;
         CK(cudaGetLastError());
     }
@@ -819,8 +1033,8 @@ void psim_destroy(PsimStepper* s) {
     cudaFree(s->block_sum);
     cudaFree(s->rank);
     cudaFree(s->perm);
-    cudaFree(s->tile_first);
-    cudaFree(s->tile_last);
+    cudaFree(s->cell_id);
+    cudaFree(s->tiles);
     cudaFree(s->staging);
     if (s->h_total) cudaFreeHost(s->h_total);
     if (s->snapshot_ready) cudaEventDestroy(s->snapshot_ready);
@@ -889,20 +1103,21 @@ int psim_create(const PsimConfig* config, PsimStepper** out) {
     CKC(cudaEventCreateWithFlags(&st->snapshot_ready, cudaEventDisableTiming));
     CKC(cudaEventCreateWithFlags(&st->snapshot_consumed, cudaEventDisableTiming));
     for (int k = 0; k < 2; ++k) {
-        CKC(cudaMalloc(&st->pos[k], sizeof(uint2) * cap));
+        CKC(cudaMalloc(&st->pos[k], sizeof(uint2) * (cap + kPadParticles)));
+        CKC(cudaMemset(st->pos[k], 0, sizeof(uint2) * (cap + kPadParticles)));
         CKC(cudaMalloc(&st->vel[k], sizeof(float2) * cap));
         CKC(cudaMalloc(&st->ty[k], sizeof(int32_t) * cap));
     }
-    CKC(cudaMalloc(&st->cell_start, sizeof(uint32_t) * ((size_t)g.cells + 1)));
+    CKC(cudaMalloc(&st->cell_start, sizeof(uint32_t) * ((size_t)g.cells + 1 + kPadCells)));
     CKC(cudaMalloc(&st->cell_count, sizeof(uint32_t) * (size_t)g.cells));
     CKC(cudaMalloc(&st->block_sum, sizeof(uint32_t) * (size_t)div_up(g.cells, kScanBlock)));
     CKC(cudaMalloc(&st->rank, sizeof(uint32_t) * cap));
     CKC(cudaMalloc(&st->perm, sizeof(uint32_t) * cap));
-    CKC(cudaMalloc(&st->tile_first, sizeof(uint32_t) * (size_t)div_up((uint32_t)cap, kTile)));
-    CKC(cudaMalloc(&st->tile_last, sizeof(uint32_t) * (size_t)div_up((uint32_t)cap, kTile)));
+    CKC(cudaMalloc(&st->cell_id, sizeof(uint32_t) * cap));
+    CKC(cudaMalloc(&st->tiles, sizeof(TileDesc) * (size_t)div_up((uint32_t)cap, kTile)));
     CKC(cudaMalloc(&st->staging, sizeof(Particle) * cap));
     CKC(cudaMallocHost(&st->h_total, sizeof(uint32_t)));
-    CKC(cudaMemset(st->cell_start, 0, sizeof(uint32_t) * ((size_t)g.cells + 1)));
+    CKC(cudaMemset(st->cell_start, 0, sizeof(uint32_t) * ((size_t)g.cells + 1 + kPadCells)));
 #undef CKC
     *out = st;
     return PSIM_OK;

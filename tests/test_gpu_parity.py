@@ -197,7 +197,13 @@ def test_single_step_midsize_liquid_vs_oracle(Stepper):
 @pytest.mark.parametrize("mie", [(3.404e-10, 117.84 * 1.380649e-23, 12.085, 6.0),   # argon: other n
                                  (3.609e-10, 1.46e-21, 12.0, 6.0),                  # Lennard-Jones 12-6
                                  (3.3e-10, 1.1e-21, 11.3, 6.5),                     # fractional m
-                                 (3.609e-10, 1.46e-21, 9.0, 4.0)])                  # odd n, small m
+                                 (3.609e-10, 1.46e-21, 9.0, 4.0),                   # odd n, small m
+                                 (3.609e-10, 1.46e-21, 16.4, 6.0),                  # q^9 * 2^z through MUFU.EX2
+                                 (3.609e-10, 1.46e-21, 14.3, 6.0),                  # q^8, rest too big for the cubic
+                                 (3.609e-10, 1.46e-21, 10.0, 6.0),                  # q^6, no rest
+                                 (3.609e-10, 1.46e-21, 18.2, 6.0),                  # q^10
+                                 (3.609e-10, 1.46e-21, 8.1, 6.0),                   # q^5 and a small rest
+                                 (3.609e-10, 1.46e-21, 24.0, 6.0)])                 # beyond the compile-time powers
 def test_single_step_other_mie_parameters_vs_oracle(mie, Stepper):
     fb = FrameBuffer(60 * 60)
     fb.metadata["particles"][0] = mie
