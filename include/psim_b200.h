@@ -25,6 +25,9 @@ extern "C" {
 #define PSIM_ECUDA (-2)    /* a CUDA runtime call or kernel failed               */
 #define PSIM_ECAPACITY (-3)/* more live particles than PsimConfig.max_particles  */
 #define PSIM_ESTATE (-4)   /* call made in the wrong state (e.g. no scene yet)   */
+#define PSIM_ENCCL (-5)    /* NCCL could not be loaded or an NCCL call failed    */
+#define PSIM_EMIGRATION (-6) /* a particle moved past the adjacent slab between two re-bins, or more
+                                particles changed slab in one re-bin than migrant_capacity */
 
 /* Step / re-bin schedules. */
 #define PSIM_SCHEDULE_REFERENCE 0 /* `S M S*17 M S*17 ...`, countdown restarts every frame, may run
@@ -33,6 +36,7 @@ extern "C" {
                                      the counter carries over between frames                     */
 
 typedef struct PsimStepper PsimStepper; /* opaque */
+typedef struct PsimGroup PsimGroup;     /* opaque: all slabs of a decomposition inside one process */
 
 typedef struct PsimConfig {
     uint32_t grid_x_log2;   /* cells in x = 1 << grid_x_log2 (reference: BUCKETS_X_LOG2 = 6, kernel.cuh:15) */
@@ -41,8 +45,16 @@ typedef struct PsimConfig {
     uint32_t schedule;      /* PSIM_SCHEDULE_*                                                             */
     uint32_t rebin_every;   /* native schedule only; 0 => 17 (the reference's effective cadence)           */
     int32_t device;         /* CUDA device ordinal; -1 => current device                                   */
-    uint32_t use_graph;     /* 1 => capture each frame's launches into a CUDA graph and replay it          */
-    uint32_t _reserved[5];
+    uint32_t use_graph;     /* reserved, must be 0                                                         */
+    /* Slab decomposition over cell rows (the reference is single-device). The grid
+     * above is the GLOBAL grid; this stepper owns rows [slab_rank, slab_rank + 1) * (cells in y / slab_count)
+     * and keeps one ghost row of each adjacent slab. max_particles is the capacity of the slab. */
+    uint32_t slab_rank;        /* 0 .. slab_count-1                                                        */
+    uint32_t slab_count;       /* 0 or 1 => the whole grid                                                 */
+    uint32_t ghost_capacity;   /* particles one ghost row can hold; 0 => 4x the slab's mean row, >= 4096   */
+    uint32_t migrant_capacity; /* particles that can move to ONE neighbour slab in one re-bin; 0 => same   */
+    uint32_t ingest_capacity;  /* records an uploaded frame can hold (a slab is usually handed the whole
+                                  scene and keeps its own rows); 0 => max_particles                        */
 } PsimConfig;
 
 /* Defaults: 64x64 cells (the reference grid), 65536 particles, reference schedule, device -1. */
@@ -108,10 +120,54 @@ int psim_get_cell_start(PsimStepper* s, uint32_t* out);
 int psim_enable_step_timing(PsimStepper* s, int enable);
 int psim_get_step_timing(PsimStepper* s, double* total_ms, uint64_t* launches);
 
+/* Where this stepper's slab sits and what it currently holds. */
+typedef struct PsimSlabInfo {
+    uint32_t slab_rank, slab_count;
+    uint32_t first_row, rows;             /* owned cell rows (global numbering)                       */
+    uint32_t first_local_row, local_rows; /* rows of psim_get_cell_start: owned + ghost rows          */
+    uint32_t particles;                   /* owned                                                    */
+    uint32_t ghost_below, ghost_above;    /* particles currently in the two ghost rows                */
+    uint32_t ghost_capacity, migrant_capacity;
+    uint32_t _reserved[5];
+} PsimSlabInfo;
+int psim_slab_info(const PsimStepper* s, PsimSlabInfo* out);
+
 /* Device pointers of the live state (cell-sorted structure of arrays), for zero-copy consumers.
  * pos: uint2[n] fixed-point (x, y); vel: float2[n]; ty: int32[n]; cell_start: uint32[cells+1]. */
 int psim_device_state(PsimStepper* s, const void** pos, const void** vel, const void** ty,
                       const void** cell_start);
+
+/* ---- slab decomposition, one process per slab (one GPU each): NCCL over NVLink -----------------
+ * Every rank creates its stepper with slab_rank = its rank and slab_count = world size, then joins the
+ * communicator. After that the ordinary calls above are COLLECTIVE: every rank makes the same sequence
+ * of psim_upload_frame / psim_step_async / psim_rebin_async / psim_run_frame_async calls. Per step each
+ * slab sends the positions of its two boundary cell rows to the adjacent slabs (halo exchange); at a
+ * re-bin, particles whose row left the slab migrate to the adjacent slab. Results are bit-identical to
+ * a single-slab run of the same scene. psim_upload_frame may be handed the whole scene (records outside
+ * the slab's rows are skipped); psim_download_frame returns the slab's own particles, and the slabs'
+ * frames concatenated in rank order are the single-slab frame.
+ * NCCL (libnccl.so.2, or $PSIM_NCCL_LIB) is loaded on first use; a single-slab user never needs it. */
+int psim_comm_unique_id(void* out128);                         /* rank 0: ncclGetUniqueId, 128 bytes    */
+int psim_comm_init(PsimStepper* s, const void* unique_id128);  /* all ranks: ncclCommInitRank           */
+
+/* ---- slab decomposition inside one process on one device ----------------------------------------
+ * The same slabs, exchanges done by device-to-device copies on one stream. It validates the
+ * decomposition (bit-identical to the single-slab run) on a single GPU. `steppers[r]` must have been
+ * created with slab_rank = r, slab_count = count and equal grids, schedules and capacities; while they
+ * belong to a group they are driven through the group calls only (download / introspection excepted). */
+int psim_group_create(PsimStepper* const* steppers, uint32_t count, PsimGroup** out);
+void psim_group_destroy(PsimGroup* g); /* does not destroy the steppers */
+const char* psim_group_last_error(const PsimGroup* g);
+int psim_group_upload_frame(PsimGroup* g, const FrameHeader* frame);
+int psim_group_set_metadata(PsimGroup* g, const FrameMetadata* meta);
+int psim_group_run_frame_async(PsimGroup* g);
+int psim_group_step_async(PsimGroup* g, uint32_t steps);
+int psim_group_rebin_async(PsimGroup* g);
+int psim_group_snapshot_async(PsimGroup* g);
+int psim_group_sync(PsimGroup* g);
+uint32_t psim_group_particle_count(const PsimGroup* g);
+/* All slabs' snapshots concatenated in rank order: the frame a single-slab stepper would return. */
+int psim_group_download_frame(PsimGroup* g, FrameHeader* dst);
 
 #ifdef __cplusplus
 } /* extern "C" */

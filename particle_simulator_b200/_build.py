@@ -57,7 +57,7 @@ def build_psim(force: bool = False, verbose: bool = False) -> str:
     deps = src + [os.path.join(INCLUDE, "psim_b200.h"), os.path.join(INCLUDE, "particle_io.h")]
     if force or _stale(LIB_PSIM, deps):
         cmd = [_nvcc(), *NVCC_ARCH, "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC", "-shared",
-               "-I" + INCLUDE, *src, "-o", LIB_PSIM]
+               "-I" + INCLUDE, *src, "-o", LIB_PSIM, "-ldl"]
         if verbose:
             cmd[1:1] = ["-Xptxas", "-v"]
         _run(cmd)

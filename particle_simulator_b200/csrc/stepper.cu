@@ -19,11 +19,13 @@
 //
 // There is no CPU path in this file and nothing here includes or links oracle/.
 #include <cuda_runtime.h>
+#include <dlfcn.h>
 
 #include <algorithm>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <string>
@@ -43,16 +45,23 @@ constexpr int kPosCap = 640;      // neighbour positions staged per stencil row 
 constexpr int kScanItems = 8;     // cells per thread in the scan kernels
 constexpr int kScanThreads = 256;
 constexpr int kScanBlock = kScanItems * kScanThreads;
-constexpr uint32_t kNoKey = 0xFFFFFFFFu;
 constexpr int kPadCells = 8;      // readable slack after cell_start[cells] for 16-byte bulk copies
 constexpr int kPadParticles = 4;  // readable slack after pos[n] for 16-byte bulk copies
 
 struct Grid {
-    uint32_t lx, ly;    // log2 cells in x / y
-    uint32_t bx, by;    // cells in x / y
-    uint32_t cells;     // bx * by
-    uint32_t sx, sy;    // 32 - lx, 32 - ly (shift that maps a fixed-point coordinate to its cell)
+    uint32_t lx;         // log2 cells in x
+    uint32_t bx;         // cells in x
+    uint32_t by;         // LOCAL cell rows held by this stepper (owned rows + ghost rows)
+    uint32_t cells;      // bx * by (local)
+    uint32_t sx, sy;     // 32 - log2(cells in x / GLOBAL cells in y): fixed-point coordinate -> global cell
+    int32_t row_offset;  // local row = global row - row_offset
+    uint32_t own_row0;   // first owned local row (1 when there is a lower ghost row, else 0)
+    uint32_t own_rows;   // owned rows
 };
+
+// Where a position falls relative to the rows this stepper owns.
+constexpr uint32_t kKeyDown = 0xFFFFFFFEu;  // below the slab: migrates to the lower neighbour
+constexpr uint32_t kKeyUp = 0xFFFFFFFDu;    // above the slab: migrates to the upper neighbour
 
 // How the non-integer part of the repulsive exponent is evaluated (see pair2 below).
 enum FracMode { kFracNone = 0, kFracPoly = 1, kFracEx2 = 2 };
@@ -132,9 +141,13 @@ __device__ __forceinline__ float2 powi2(float2 b, int k) {  // k is uniform acro
     return r;
 }
 
+// Local cell of a position (kernel.cuh:224-226 with the slab's row offset), or kKeyDown / kKeyUp when
+// the position lies outside the owned rows. With a single slab every position is inside.
 __device__ __forceinline__ uint32_t cell_of(uint2 p, const Grid& g) {
-    // kernel.cuh:224-226
-    return (p.x >> g.sx) + ((p.y >> g.sy) << g.lx);
+    int32_t row = (int32_t)(p.y >> g.sy) - g.row_offset;
+    if (row < (int32_t)g.own_row0) return kKeyDown;
+    if (row >= (int32_t)(g.own_row0 + g.own_rows)) return kKeyUp;
+    return (p.x >> g.sx) + ((uint32_t)row << g.lx);
 }
 
 // mbarrier + 1-D bulk copy (TMA) wrappers: global -> shared::cta, completion counted in bytes.
@@ -318,7 +331,7 @@ struct StepArgs {
     const uint32_t* __restrict__ cell_id;
     const uint32_t* __restrict__ cell_start;
     const TileDesc* __restrict__ tiles;
-    uint32_t n;
+    uint32_t own_lo, own_hi;  // the particles this stepper steps: [own_lo, own_hi) (ghost rows lie outside)
     Grid g;
     Phys ph;
 };
@@ -358,7 +371,7 @@ __global__ void __launch_bounds__(kTile, 8) step_kernel(const StepArgs a) {
     __shared__ __align__(8) uint64_t s_bar;
 
     const uint32_t b = blockIdx.x;
-    const uint32_t i = b * kTile + threadIdx.x;
+    const uint32_t i = a.own_lo + b * kTile + threadIdx.x;
     const TileDesc t = a.tiles[b];
 
     if (t.fits) {
@@ -376,7 +389,7 @@ __global__ void __launch_bounds__(kTile, 8) step_kernel(const StepArgs a) {
         }
         __syncthreads();  // the barrier is initialised before anyone polls it
     }
-    const bool live = i < a.n;
+    const bool live = i < a.own_hi;
     uint2 pi = make_uint2(0, 0);
     float2 vi = make_float2(0.f, 0.f);
     uint32_t cell = 0;
@@ -405,38 +418,73 @@ __global__ void __launch_bounds__(kTile, 8) step_kernel(const StepArgs a) {
 //
 //   key_count : key = cell(pos); rank = atomicAdd(count[key], 1)          (arbitrary rank in cell)
 //   scan      : cell_start = exclusive prefix sum of count                 (3 small kernels)
-//   scatter   : perm[cell_start[key] + rank] = source index
-//   gather    : slot p holds source index i = perm[p]; its final place inside its cell is the number
-//               of cell-mates with a smaller source index, which makes the result the STABLE sort
+//   scatter   : perm[cell_start[key] + rank] = candidate index
+//   gather    : slot p holds candidate c = perm[p]; its final place inside its cell is the number of
+//               cell-mates with a smaller candidate index, which makes the result the STABLE sort
 //               whatever order the atomics were served in -- the order the reference's serial
 //               append (kernel.cuh:219-229) and its (row, column, slot) pull (kernel_bucket.cuh:17-33)
 //               both produce.
+// The candidates are, in this order: wire-format records ahead of the live state (an ingested frame,
+// or the particles that migrated in from the lower slab), the live particles this stepper owns, and
+// records behind them (migrants from the upper slab) -- the order those particles have in the global
+// cell-sorted array, so that a slab-decomposed run sorts exactly like a single-slab one.
 // ------------------------------------------------------------------------------------------------
 
-struct Source {  // where the particles to be binned come from
-    const Particle* aos;  // ingest: records as they arrived (may contain nulls, ty < 0)
-    const uint2* pos;     // re-bin: the live state
+struct Source {
+    const Particle* aos_lo;  // records that sort ahead of the live state (may contain nulls, ty < 0)
+    uint32_t n_lo;
+    const uint2* pos;  // the live state, particles [soa_lo, soa_lo + n_soa)
     const float2* vel;
     const int32_t* ty;
+    uint32_t soa_lo, n_soa;
+    const Particle* aos_hi;  // records that sort behind it
+    uint32_t n_hi;
+    uint32_t strict;  // 1: a record outside the owned rows is an error (migrants), 0: it is skipped (ingest)
 };
 
-template <bool AOS>
-__device__ __forceinline__ uint32_t source_key(const Source& s, uint32_t i, const Grid& g) {
-    if (AOS) {
-        const Particle& p = s.aos[i];
-        if (p.ty < 0) return kNoKey;  // kernel.cuh:222
-        return cell_of(make_uint2(p.x, p.y), g);
+__device__ __forceinline__ uint32_t source_count(const Source& s) { return s.n_lo + s.n_soa + s.n_hi; }
+
+// Position / velocity / label of candidate c; returns false for a null record (kernel.cuh:222).
+__device__ __forceinline__ bool source_fetch(const Source& s, uint32_t c, uint2& pos, float2& vel, int32_t& ty,
+                                             bool& is_record) {
+    const Particle* rec = nullptr;
+    if (c < s.n_lo) rec = s.aos_lo + c;
+    else if (c >= s.n_lo + s.n_soa) rec = s.aos_hi + (c - s.n_lo - s.n_soa);
+    is_record = rec != nullptr;
+    if (rec) {
+        Particle q = *rec;
+        pos = make_uint2(q.x, q.y);
+        vel = make_float2(q.vx, q.vy);
+        ty = q.ty;
+        return q.ty >= 0;
     }
-    return cell_of(s.pos[i], g);
+    uint32_t i = s.soa_lo + (c - s.n_lo);
+    pos = s.pos[i];
+    vel = s.vel[i];
+    ty = s.ty[i];
+    return true;
 }
 
-template <bool AOS>
-__global__ void key_count_kernel(Source src, uint32_t count, Grid g, uint32_t* __restrict__ cell_count,
-                                 uint32_t* __restrict__ rank) {
-    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= count) return;
-    uint32_t key = source_key<AOS>(src, i, g);
-    if (key != kNoKey) rank[i] = atomicAdd(&cell_count[key], 1u);
+// device-side error bits (PsimStepper::d_flags[0])
+constexpr uint32_t kErrMigrantOutside = 1u;   // a migrant record does not belong to this slab
+constexpr uint32_t kErrMigrantOverflow = 2u;  // more migrants than the exchange boxes hold
+constexpr uint32_t kErrMigrantTooFar = 4u;    // a particle left for a slab that is not adjacent
+
+__global__ void key_count_kernel(Source src, Grid g, uint32_t* __restrict__ cell_count, uint32_t* __restrict__ rank,
+                                 uint32_t* __restrict__ flags) {
+    uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= source_count(src)) return;
+    uint2 pos;
+    float2 vel;
+    int32_t ty;
+    bool is_record;
+    if (!source_fetch(src, c, pos, vel, ty, is_record)) return;
+    uint32_t key = cell_of(pos, g);
+    if (key >= kKeyUp) {  // outside the owned rows: filtered (ingest) or already extracted (live state)
+        if (is_record && src.strict) atomicOr(flags, kErrMigrantOutside);
+        return;
+    }
+    rank[c] = atomicAdd(&cell_count[key], 1u);
 }
 
 __global__ void __launch_bounds__(kScanThreads) scan_reduce_kernel(const uint32_t* __restrict__ in, uint32_t count,
@@ -521,40 +569,37 @@ __global__ void __launch_bounds__(kScanThreads) scan_apply_kernel(const uint32_t
     }
 }
 
-template <bool AOS>
-__global__ void scatter_kernel(Source src, uint32_t count, Grid g, const uint32_t* __restrict__ cell_start,
+__global__ void scatter_kernel(Source src, Grid g, const uint32_t* __restrict__ cell_start,
                                const uint32_t* __restrict__ rank, uint32_t* __restrict__ perm) {
-    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= count) return;
-    uint32_t key = source_key<AOS>(src, i, g);
-    if (key != kNoKey) perm[cell_start[key] + rank[i]] = i;
-}
-
-template <bool AOS>
-__global__ void gather_kernel(Source src, uint32_t live, Grid g, const uint32_t* __restrict__ cell_start,
-                              const uint32_t* __restrict__ perm, uint2* __restrict__ pos_out,
-                              float2* __restrict__ vel_out, int32_t* __restrict__ ty_out,
-                              uint32_t* __restrict__ cell_id_out) {
-    uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
-    if (p >= live) return;
-    uint32_t i = perm[p];
+    uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= source_count(src)) return;
     uint2 pos;
     float2 vel;
     int32_t ty;
-    if (AOS) {
-        Particle q = src.aos[i];
-        pos = make_uint2(q.x, q.y);
-        vel = make_float2(q.vx, q.vy);
-        ty = q.ty;
-    } else {
-        pos = src.pos[i];
-        vel = src.vel[i];
-        ty = src.ty[i];
-    }
+    bool is_record;
+    if (!source_fetch(src, c, pos, vel, ty, is_record)) return;
+    uint32_t key = cell_of(pos, g);
+    if (key >= kKeyUp) return;
+    perm[cell_start[key] + rank[c]] = c;
+}
+
+// Slots [p_lo, p_hi) of the sorted arrays are the owned rows; ghost rows are filled by the exchange.
+__global__ void gather_kernel(Source src, uint32_t p_lo, uint32_t p_hi, Grid g,
+                              const uint32_t* __restrict__ cell_start, const uint32_t* __restrict__ perm,
+                              uint2* __restrict__ pos_out, float2* __restrict__ vel_out,
+                              int32_t* __restrict__ ty_out, uint32_t* __restrict__ cell_id_out) {
+    uint32_t p = p_lo + blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= p_hi) return;
+    uint32_t c = perm[p];
+    uint2 pos;
+    float2 vel;
+    int32_t ty;
+    bool is_record;
+    source_fetch(src, c, pos, vel, ty, is_record);
     uint32_t key = cell_of(pos, g);
     uint32_t s = cell_start[key], e = cell_start[key + 1];
     uint32_t r = 0;
-    for (uint32_t k = s; k < e; ++k) r += perm[k] < i ? 1u : 0u;
+    for (uint32_t k = s; k < e; ++k) r += perm[k] < c ? 1u : 0u;
     uint32_t dst = s + r;
     pos_out[dst] = pos;
     vel_out[dst] = vel;
@@ -562,15 +607,32 @@ __global__ void gather_kernel(Source src, uint32_t live, Grid g, const uint32_t*
     cell_id_out[dst] = key;
 }
 
-// One descriptor per tile of kTile consecutive particles: the cell range of the tile, and for each of
-// the three stencil rows the (16-byte aligned) slices of cell_start and of the position array that its
+// The few numbers the host needs after a binning: where the owned rows and their two boundary rows
+// start and end in the sorted arrays. out[0] = own_lo, [1] = end of the first owned row,
+// [2] = start of the last owned row, [3] = own_hi, [4] = total (with ghost rows), [5] = error flags.
+__global__ void slab_counts_kernel(const uint32_t* __restrict__ cell_start, Grid g, const uint32_t* __restrict__ flags,
+                                   uint32_t* __restrict__ out) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    out[0] = cell_start[g.own_row0 * g.bx];
+    out[1] = cell_start[(g.own_row0 + 1) * g.bx];
+    out[2] = cell_start[(g.own_row0 + g.own_rows - 1) * g.bx];
+    out[3] = cell_start[(g.own_row0 + g.own_rows) * g.bx];
+    out[4] = cell_start[g.cells];
+    out[5] = flags[0];
+}
+
+// Cell ids of a ghost row: its particles arrive as bare positions; the ids are needed by nobody (ghosts
+// are never stepped) -- but the row's cell_start entries are, and those come from the scan.
+
+// One descriptor per tile of kTile consecutive OWNED particles: the cell range of the tile, and for each
+// of the three stencil rows the (16-byte aligned) slices of cell_start and of the position array that its
 // CTA stages in shared memory (see step_kernel).
-__global__ void tile_desc_kernel(const uint32_t* __restrict__ cell_start, Grid g, uint32_t n,
+__global__ void tile_desc_kernel(const uint32_t* __restrict__ cell_start, Grid g, uint32_t own_lo, uint32_t own_hi,
                                  TileDesc* __restrict__ tiles) {
     uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
-    uint32_t ntiles = (n + kTile - 1) / kTile;
+    uint32_t ntiles = (own_hi - own_lo + kTile - 1) / kTile;
     if (b >= ntiles) return;
-    uint32_t i0 = b * kTile, i1 = min(n, i0 + kTile) - 1;
+    uint32_t i0 = own_lo + b * kTile, i1 = min(own_hi, i0 + kTile) - 1;
     TileDesc t;
     t.first = (uint32_t)last_le(cell_start, (int)g.cells, i0);
     t.last = (uint32_t)last_le(cell_start, (int)g.cells, i1);
@@ -598,11 +660,11 @@ __global__ void tile_desc_kernel(const uint32_t* __restrict__ cell_start, Grid g
     tiles[b] = t;
 }
 
-// snapshot: pack the structure of arrays back into wire-format records (particle.rs:10-18)
+// snapshot: pack the owned particles back into wire-format records (particle.rs:10-18)
 __global__ void pack_kernel(const uint2* __restrict__ pos, const float2* __restrict__ vel,
-                            const int32_t* __restrict__ ty, uint32_t n, Particle* __restrict__ out) {
-    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
+                            const int32_t* __restrict__ ty, uint32_t lo, uint32_t hi, Particle* __restrict__ out) {
+    uint32_t i = lo + blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= hi) return;
     uint2 p = pos[i];
     float2 v = vel[i];
     Particle q;
@@ -611,7 +673,67 @@ __global__ void pack_kernel(const uint2* __restrict__ pos, const float2* __restr
     q.vx = v.x;
     q.vy = v.y;
     q.ty = ty[i];
-    out[i] = q;
+    out[i - lo] = q;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Migration between slabs at re-bin time: owned particles whose position left the owned rows are
+// collected (atomics, arbitrary order), then written to a fixed-size box in ascending index order
+// (= the order they have in the global sorted array) for the neighbour to merge.
+// ------------------------------------------------------------------------------------------------
+
+struct MigrantBoxHeader {
+    uint32_t count;
+    uint32_t _pad[3];
+};
+
+__global__ void migrant_extract_kernel(const uint2* __restrict__ pos, uint32_t own_lo, uint32_t own_hi, Grid g,
+                                       uint32_t box_capacity, uint32_t* __restrict__ counters,
+                                       uint32_t* __restrict__ idx_down, uint32_t* __restrict__ idx_up,
+                                       uint32_t* __restrict__ flags) {
+    uint32_t i = own_lo + blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= own_hi) return;
+    uint2 p = pos[i];
+    uint32_t key = cell_of(p, g);
+    if (key < kKeyUp) return;
+    int32_t row = (int32_t)(p.y >> g.sy) - g.row_offset;
+    // the neighbours' slabs are as tall as this one: anything beyond them cannot be delivered
+    if (row < (int32_t)g.own_row0 - (int32_t)g.own_rows || row >= (int32_t)(g.own_row0 + 2 * g.own_rows))
+        atomicOr(flags, kErrMigrantTooFar);
+    uint32_t dir = key == kKeyDown ? 0u : 1u;
+    uint32_t slot = atomicAdd(&counters[dir], 1u);
+    if (slot >= box_capacity) {
+        atomicOr(flags, kErrMigrantOverflow);
+        return;
+    }
+    (dir == 0 ? idx_down : idx_up)[slot] = i;
+}
+
+__global__ void migrant_pack_kernel(const uint2* __restrict__ pos, const float2* __restrict__ vel,
+                                    const int32_t* __restrict__ ty, const uint32_t* __restrict__ counter,
+                                    const uint32_t* __restrict__ idx, uint32_t box_capacity,
+                                    unsigned char* __restrict__ box) {
+    uint32_t count = min(*counter, box_capacity);
+    MigrantBoxHeader* header = reinterpret_cast<MigrantBoxHeader*>(box);
+    Particle* rec = reinterpret_cast<Particle*>(box + sizeof(MigrantBoxHeader));
+    uint32_t e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e == 0) {
+        header->count = count;
+        header->_pad[0] = header->_pad[1] = header->_pad[2] = 0;
+    }
+    if (e >= count) return;
+    uint32_t i = idx[e];
+    uint32_t r = 0;
+    for (uint32_t k = 0; k < count; ++k) r += idx[k] < i ? 1u : 0u;
+    Particle q;
+    uint2 p = pos[i];
+    float2 v = vel[i];
+    q.x = p.x;
+    q.y = p.y;
+    q.vx = v.x;
+    q.vy = v.y;
+    q.ty = ty[i];
+    rec[r] = q;
 }
 
 }  // namespace
@@ -620,42 +742,97 @@ __global__ void pack_kernel(const uint2* __restrict__ pos, const float2* __restr
 // Host side
 // ------------------------------------------------------------------------------------------------
 
+// NCCL is bound at run time (dlopen) and only when psim_comm_init is called: a single-GPU user of this
+// library needs no NCCL. Minimal declarations of the stable NCCL 2.x C API.
+typedef struct ncclComm* ncclComm_t;
+typedef struct {
+    char internal[128];
+} ncclUniqueId;
+constexpr int kNcclUint8 = 1;  // ncclDataType_t::ncclUint8
+
+struct NcclApi {
+    void* lib = nullptr;
+    int (*GetUniqueId)(ncclUniqueId*) = nullptr;
+    int (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+    int (*CommDestroy)(ncclComm_t) = nullptr;
+    int (*Send)(const void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+    int (*Recv)(void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+    int (*GroupStart)() = nullptr;
+    int (*GroupEnd)() = nullptr;
+    const char* (*GetErrorString)(int) = nullptr;
+};
+
+// What one rank sends to / receives from its lower ([0]) and upper ([1]) neighbour slab.
+struct XferOp {
+    const void* send[2] = {nullptr, nullptr};
+    void* recv[2] = {nullptr, nullptr};
+    size_t send_bytes[2] = {0, 0};
+    size_t recv_bytes[2] = {0, 0};
+};
+
+struct PsimGroup;
+
 struct PsimStepper {
     PsimConfig cfg{};
     Grid grid{};
     Phys phys{};
-    int kernel_kn = 0;         // step-kernel variant: integer part of n/2+1 (0: run-time exponents)
+    int kernel_kn = 0;  // step-kernel variant: integer part of n/2+1 (0: run-time exponents)
     int kernel_frac = kFracEx2;
     bool kernel_aniso = false;
     FrameMetadata meta{};
     int device = 0;
 
+    // slab decomposition (nranks == 1: the whole grid, no ghost rows, no exchange)
+    int rank = 0, nranks = 1;
+    ncclComm_t comm = nullptr;   // one process per slab (psim_comm_init)
+    PsimGroup* group = nullptr;  // all slabs in this process (psim_group_create)
+
     cudaStream_t own_stream = nullptr;
-    cudaStream_t stream = nullptr;       // where the step loop runs (own_stream or the caller's)
+    cudaStream_t stream = nullptr;       // where the step loop runs (own_stream, the caller's, or the group's)
     cudaStream_t copy_stream = nullptr;  // snapshot download
     cudaEvent_t snapshot_ready = nullptr;
     cudaEvent_t snapshot_consumed = nullptr;
 
-    // live state
+    // capacities
+    uint32_t ghost_cap = 0;     // particles per ghost row
+    uint32_t cap_total = 0;     // max_particles + 2 * ghost_cap
+    uint32_t box_capacity = 0;  // migrants per direction per re-bin
+    size_t box_bytes = 0;
+
+    // live state (see the layout table at the top of this file)
     uint2* pos[2] = {nullptr, nullptr};
     float2* vel[2] = {nullptr, nullptr};
     int32_t* ty[2] = {nullptr, nullptr};
     int cur_pos = 0, cur_vel = 0, cur_ty = 0;
-    uint32_t* cell_start = nullptr;  // cells + 1
+    uint32_t* cell_id = nullptr;
+    TileDesc* tiles = nullptr;
+    uint32_t* cell_start = nullptr;  // cells + 1 (+ padding)
     uint32_t* cell_count = nullptr;  // cells
     uint32_t* block_sum = nullptr;
-    uint32_t* rank = nullptr;
+    uint32_t* rank_in_cell = nullptr;
     uint32_t* perm = nullptr;
-    uint32_t* cell_id = nullptr;  // n: cell of every particle as of the last binning
-    TileDesc* tiles = nullptr;    // ceil(n / kTile)
-    Particle* staging = nullptr;  // ingest (AoS) and snapshot (AoS) buffer
-    uint32_t* h_total = nullptr;  // pinned
+    Particle* staging = nullptr;   // ingest buffer (wire-format records)
+    Particle* snapshot = nullptr;  // packed snapshot of the owned particles (wire-format records)
+    uint32_t ingest_cap = 0;       // records the ingest buffer holds
+    unsigned char* outbox[2] = {nullptr, nullptr};
+    unsigned char* inbox[2] = {nullptr, nullptr};
+    uint32_t* mig_counters = nullptr;  // 2
+    uint32_t* mig_idx[2] = {nullptr, nullptr};
+    uint32_t* d_flags = nullptr;   // 1
+    uint32_t* d_counts = nullptr;  // 8
+    uint32_t* h_counts = nullptr;  // pinned, 16
 
-    uint32_t n = 0;            // live particles
-    uint32_t snapshot_n = 0;   // particles in the packed snapshot
+    uint32_t n = 0;        // particles this stepper owns
+    uint32_t n_total = 0;  // with ghost rows
+    uint32_t own_lo = 0, own_hi = 0, b_lo_end = 0, b_hi_start = 0;
+    Source src{};          // candidates of the binning in flight
+    bool binning_is_ingest = false;
+
+    uint32_t snapshot_n = 0;
     FrameMetadata snapshot_meta{};
     bool has_scene = false;
     bool has_snapshot = false;
+    bool fresh_scene = false;  // nothing has been stepped since the ingest: the binning is current
     int native_countdown = 0;  // native schedule: steps until the next re-bin
 
     uint64_t steps_executed = 0, rebins_executed = 0, launches = 0;
@@ -669,9 +846,17 @@ struct PsimStepper {
     std::string error;
 };
 
+struct PsimGroup {
+    std::vector<PsimStepper*> ranks;
+    cudaStream_t stream = nullptr;
+    int native_countdown = 0;
+    std::string error;
+};
+
 namespace {
 
 std::string g_create_error;
+NcclApi g_nccl;
 
 int fail(PsimStepper* s, int code, const char* fmt, ...) {
     char buf[512];
@@ -691,6 +876,16 @@ int fail(PsimStepper* s, int code, const char* fmt, ...) {
             return fail(s, PSIM_ECUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(err__), __FILE__, \
                         __LINE__);                                                                        \
     } while (0)
+
+#define CKN(call)                                                                                      \
+    do {                                                                                               \
+        int err__ = (call);                                                                            \
+        if (err__ != 0)                                                                                \
+            return fail(s, PSIM_ENCCL, "%s failed: %s (%s:%d)", #call,                                 \
+                        g_nccl.GetErrorString ? g_nccl.GetErrorString(err__) : "?", __FILE__, __LINE__); \
+    } while (0)
+
+inline uint32_t div_up(uint32_t a, uint32_t b) { return (a + b - 1) / b; }
 
 // Cubic for 2^z on z in [z_lo, z_hi] (weighted least squares on Chebyshev nodes; the constant term is
 // pinned to 1 so that z = 0 is exact). Returns the largest error of (n/m) q^(kn+fn) it causes, i.e. the
@@ -845,9 +1040,125 @@ void launch_step(PsimStepper* s, const StepArgs& a, uint32_t tiles) {
     }
 }
 
-inline uint32_t div_up(uint32_t a, uint32_t b) { return (a + b - 1) / b; }
+// ------------------------------------------------------------------------------------------------
+// Slab transports.  A "team" is the set of slabs one host thread drives in lock-step:
+//   * a lone stepper (nranks == 1: no exchange at all; nranks > 1: one process per slab, exchanges
+//     are NCCL send/recv pairs with the two adjacent ranks over NVLink), or
+//   * a PsimGroup: every slab in this process on one device and one stream; exchanges are
+//     device-to-device copies. It exists to validate the decomposition bit-for-bit on a single GPU.
+// Every exchange moves data only between adjacent slabs: [0] = lower neighbour, [1] = upper.
+// ------------------------------------------------------------------------------------------------
 
-// cell_start = exclusive scan of cell_count; total (live particles) -> cell_start[cells]
+struct Team {
+    PsimStepper* const* ranks;
+    int count;
+    PsimGroup* group;
+};
+
+bool load_nccl(PsimStepper* s) {
+    if (g_nccl.lib) return true;
+    const char* env = getenv("PSIM_NCCL_LIB");
+    const char* names[] = {env, "libnccl.so.2", "libnccl.so"};
+    void* lib = nullptr;
+    for (const char* name : names) {
+        if (!name || !*name) continue;
+        lib = dlopen(name, RTLD_NOW | RTLD_GLOBAL);
+        if (lib) break;
+    }
+    if (!lib) {
+        fail(s, PSIM_ENCCL, "cannot load NCCL (libnccl.so.2; set PSIM_NCCL_LIB): %s", dlerror());
+        return false;
+    }
+    NcclApi api;
+    api.lib = lib;
+    bool ok = true;
+    auto sym = [&](const char* name) {
+        void* p = dlsym(lib, name);
+        if (!p) ok = false;
+        return p;
+    };
+    api.GetUniqueId = reinterpret_cast<decltype(api.GetUniqueId)>(sym("ncclGetUniqueId"));
+    api.CommInitRank = reinterpret_cast<decltype(api.CommInitRank)>(sym("ncclCommInitRank"));
+    api.CommDestroy = reinterpret_cast<decltype(api.CommDestroy)>(sym("ncclCommDestroy"));
+    api.Send = reinterpret_cast<decltype(api.Send)>(sym("ncclSend"));
+    api.Recv = reinterpret_cast<decltype(api.Recv)>(sym("ncclRecv"));
+    api.GroupStart = reinterpret_cast<decltype(api.GroupStart)>(sym("ncclGroupStart"));
+    api.GroupEnd = reinterpret_cast<decltype(api.GroupEnd)>(sym("ncclGroupEnd"));
+    api.GetErrorString = reinterpret_cast<decltype(api.GetErrorString)>(sym("ncclGetErrorString"));
+    if (!ok) {
+        fail(s, PSIM_ENCCL, "the NCCL library lacks a required symbol");
+        return false;
+    }
+    g_nccl = api;
+    return true;
+}
+
+// One exchange of a lone slab with its neighbours: a grouped send/recv pair per side.
+int exchange_nccl(PsimStepper* s, const XferOp& op, cudaStream_t stream) {
+    if (!s->comm) return fail(s, PSIM_ESTATE, "slab %d of %d has no communicator: call psim_comm_init", s->rank, s->nranks);
+    bool any = false;
+    for (int dir = 0; dir < 2; ++dir) any = any || op.send_bytes[dir] || op.recv_bytes[dir];
+    if (!any) return PSIM_OK;
+    CKN(g_nccl.GroupStart());
+    for (int dir = 0; dir < 2; ++dir) {
+        int peer = dir == 0 ? s->rank - 1 : s->rank + 1;
+        if (peer < 0 || peer >= s->nranks) continue;
+        if (op.send_bytes[dir]) CKN(g_nccl.Send(op.send[dir], op.send_bytes[dir], kNcclUint8, peer, s->comm, stream));
+        if (op.recv_bytes[dir]) CKN(g_nccl.Recv(op.recv[dir], op.recv_bytes[dir], kNcclUint8, peer, s->comm, stream));
+    }
+    CKN(g_nccl.GroupEnd());
+    return PSIM_OK;
+}
+
+int team_exchange(const Team& t, const std::vector<XferOp>& ops) {
+    if (!t.group) {
+        PsimStepper* s = t.ranks[0];
+        if (s->nranks == 1) return PSIM_OK;
+        return exchange_nccl(s, ops[0], s->stream);
+    }
+    for (int r = 0; r < t.count; ++r) {
+        PsimStepper* s = t.ranks[r];
+        for (int dir = 0; dir < 2; ++dir) {
+            int peer = dir == 0 ? r - 1 : r + 1;
+            if (peer < 0 || peer >= t.count) continue;
+            if (ops[r].send_bytes[dir] != ops[peer].recv_bytes[dir ^ 1])
+                return fail(s, PSIM_EINVAL, "internal: slab %d sends %zu bytes, slab %d expects %zu", r,
+                            ops[r].send_bytes[dir], peer, ops[peer].recv_bytes[dir ^ 1]);
+            if (ops[r].send_bytes[dir])
+                CK(cudaMemcpyAsync(ops[peer].recv[dir ^ 1], ops[r].send[dir], ops[r].send_bytes[dir],
+                                   cudaMemcpyDeviceToDevice, t.group->stream));
+        }
+    }
+    return PSIM_OK;
+}
+
+inline bool has_lower(const PsimStepper* s) { return s->rank > 0; }
+inline bool has_upper(const PsimStepper* s) { return s->rank + 1 < s->nranks; }
+
+// The positions of this slab's two boundary rows go to the neighbours' ghost rows of the same buffer.
+XferOp ghost_positions_op(PsimStepper* s) {
+    XferOp op;
+    uint2* pos = s->pos[s->cur_pos];
+    if (has_lower(s)) {
+        op.send[0] = pos + s->own_lo;
+        op.send_bytes[0] = sizeof(uint2) * (size_t)(s->b_lo_end - s->own_lo);
+        op.recv[0] = pos;
+        op.recv_bytes[0] = sizeof(uint2) * (size_t)s->own_lo;
+    }
+    if (has_upper(s)) {
+        op.send[1] = pos + s->b_hi_start;
+        op.send_bytes[1] = sizeof(uint2) * (size_t)(s->own_hi - s->b_hi_start);
+        op.recv[1] = pos + s->own_hi;
+        op.recv_bytes[1] = sizeof(uint2) * (size_t)(s->n_total - s->own_hi);
+    }
+    return op;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Binning, phase by phase (every phase is run for all slabs of the team before the next one starts)
+// ------------------------------------------------------------------------------------------------
+
+// cell_start = exclusive scan of cell_count; total -> cell_start[cells]
 int enqueue_scan(PsimStepper* s) {
     uint32_t cells = s->grid.cells;
     uint32_t blocks = div_up(cells, kScanBlock);
@@ -859,42 +1170,207 @@ int enqueue_scan(PsimStepper* s) {
     return PSIM_OK;
 }
 
-int enqueue_tiles(PsimStepper* s) {
+// Re-bin, phase 1 (slabs only): particles that left the owned rows go into the two outboxes.
+int bin_phase_migrants(PsimStepper* s, XferOp& op) {
+    const uint32_t tb = 256;
+    CK(cudaMemsetAsync(s->mig_counters, 0, 2 * sizeof(uint32_t), s->stream));
+    if (s->n) {
+        migrant_extract_kernel<<<div_up(s->n, tb), tb, 0, s->stream>>>(s->pos[s->cur_pos], s->own_lo, s->own_hi,
+                                                                       s->grid, s->box_capacity, s->mig_counters,
+                                                                       s->mig_idx[0], s->mig_idx[1], s->d_flags);
+        s->launches += 1;
+    }
+    for (int dir = 0; dir < 2; ++dir) {
+        migrant_pack_kernel<<<div_up(s->box_capacity, tb), tb, 0, s->stream>>>(
+            s->pos[s->cur_pos], s->vel[s->cur_vel], s->ty[s->cur_ty], s->mig_counters + dir, s->mig_idx[dir],
+            s->box_capacity, s->outbox[dir]);
+        s->launches += 1;
+    }
+    CK(cudaGetLastError());
+    if (has_lower(s)) {
+        op.send[0] = s->outbox[0];
+        op.recv[0] = s->inbox[0];
+        op.send_bytes[0] = op.recv_bytes[0] = s->box_bytes;
+    }
+    if (has_upper(s)) {
+        op.send[1] = s->outbox[1];
+        op.recv[1] = s->inbox[1];
+        op.send_bytes[1] = op.recv_bytes[1] = s->box_bytes;
+    }
+    return PSIM_OK;
+}
+
+// Phase 2: keys and per-cell counts of the candidates; the counts of the boundary rows are the
+// neighbours' ghost-row counts.
+int bin_phase_count(PsimStepper* s, const Source& src, XferOp& op) {
+    const uint32_t tb = 256;
+    s->src = src;
+    CK(cudaMemsetAsync(s->cell_count, 0, sizeof(uint32_t) * s->grid.cells, s->stream));
+    uint32_t cand = src.n_lo + src.n_soa + src.n_hi;
+    if (cand) {
+        key_count_kernel<<<div_up(cand, tb), tb, 0, s->stream>>>(src, s->grid, s->cell_count, s->rank_in_cell,
+                                                                 s->d_flags);
+        s->launches += 1;
+        CK(cudaGetLastError());
+    }
+    const Grid& g = s->grid;
+    const size_t row_bytes = sizeof(uint32_t) * g.bx;
+    if (has_lower(s)) {
+        op.send[0] = s->cell_count + (size_t)g.own_row0 * g.bx;
+        op.recv[0] = s->cell_count;
+        op.send_bytes[0] = op.recv_bytes[0] = row_bytes;
+    }
+    if (has_upper(s)) {
+        op.send[1] = s->cell_count + (size_t)(g.own_row0 + g.own_rows - 1) * g.bx;
+        op.recv[1] = s->cell_count + (size_t)(g.by - 1) * g.bx;
+        op.send_bytes[1] = op.recv_bytes[1] = row_bytes;
+    }
+    return PSIM_OK;
+}
+
+// Phase 3: offsets, and the handful of numbers the host needs to size the next launches.
+int bin_phase_scan(PsimStepper* s, bool need_counts) {
+    int rc = enqueue_scan(s);
+    if (rc) return rc;
+    if (need_counts) {
+        slab_counts_kernel<<<1, 32, 0, s->stream>>>(s->cell_start, s->grid, s->d_flags, s->d_counts);
+        s->launches += 1;
+        CK(cudaGetLastError());
+        CK(cudaMemcpyAsync(s->h_counts, s->d_counts, 8 * sizeof(uint32_t), cudaMemcpyDeviceToHost, s->stream));
+    }
+    return PSIM_OK;
+}
+
+// Host: wait for the counts (the only host synchronisation of a re-bin, and only with slabs).
+int bin_phase_commit(PsimStepper* s) {
+    CK(cudaStreamSynchronize(s->stream));
+    const uint32_t* h = s->h_counts;
+    uint32_t flags = h[5];
+    if (flags & kErrMigrantOverflow)
+        return fail(s, PSIM_EMIGRATION, "slab %d: more than %u particles left for a neighbour slab in one re-bin "
+                    "(PsimConfig.migrant_capacity)", s->rank, s->box_capacity);
+    if (flags & (kErrMigrantTooFar | kErrMigrantOutside))
+        return fail(s, PSIM_EMIGRATION, "slab %d: a particle moved past the adjacent slab between two re-bins", s->rank);
+    uint32_t owned = h[3] - h[0];
+    if (owned > s->cfg.max_particles)
+        return fail(s, PSIM_ECAPACITY, "%u live particles exceed max_particles = %u", owned, s->cfg.max_particles);
+    if (h[0] > s->ghost_cap || h[4] - h[3] > s->ghost_cap)
+        return fail(s, PSIM_ECAPACITY, "slab %d: a ghost row holds %u particles, ghost_capacity = %u", s->rank,
+                    std::max(h[0], h[4] - h[3]), s->ghost_cap);
+    s->own_lo = h[0];
+    s->b_lo_end = h[1];
+    s->b_hi_start = h[2];
+    s->own_hi = h[3];
+    s->n_total = h[4];
+    s->n = owned;
+    return PSIM_OK;
+}
+
+// Phase 4: place the owned particles (stable), flip the buffers; the new boundary rows are the
+// neighbours' ghost rows.
+int bin_phase_place(PsimStepper* s, bool ingest, XferOp& op) {
+    const uint32_t tb = 256;
+    const Source& src = s->src;
+    uint32_t cand = src.n_lo + src.n_soa + src.n_hi;
+    int np = ingest ? 0 : s->cur_pos ^ 1, nv = ingest ? 0 : s->cur_vel ^ 1, nt = ingest ? 0 : s->cur_ty ^ 1;
+    if (s->n) {
+        scatter_kernel<<<div_up(cand, tb), tb, 0, s->stream>>>(src, s->grid, s->cell_start, s->rank_in_cell, s->perm);
+        gather_kernel<<<div_up(s->n, tb), tb, 0, s->stream>>>(src, s->own_lo, s->own_hi, s->grid, s->cell_start,
+                                                              s->perm, s->pos[np], s->vel[nv], s->ty[nt], s->cell_id);
+        s->launches += 2;
+        CK(cudaGetLastError());
+    }
+    s->cur_pos = np;
+    s->cur_vel = nv;
+    s->cur_ty = nt;
+    op = ghost_positions_op(s);
+    return PSIM_OK;
+}
+
+// Phase 5: staging descriptors of the step kernel's tiles.
+int bin_phase_tiles(PsimStepper* s) {
     uint32_t tiles = div_up(s->n, kTile);
     if (tiles == 0) return PSIM_OK;
-    tile_desc_kernel<<<div_up(tiles, 128), 128, 0, s->stream>>>(s->cell_start, s->grid, s->n, s->tiles);
+    tile_desc_kernel<<<div_up(tiles, 128), 128, 0, s->stream>>>(s->cell_start, s->grid, s->own_lo, s->own_hi, s->tiles);
     s->launches += 1;
     CK(cudaGetLastError());
     return PSIM_OK;
 }
 
-// Re-bin the live state (bucket_move, kernel_bucket.cuh:5-39).
-int enqueue_rebin(PsimStepper* s) {
-    if (s->n == 0) return PSIM_OK;
-    const uint32_t n = s->n, tb = 256;
-    Source src{nullptr, s->pos[s->cur_pos], s->vel[s->cur_vel], s->ty[s->cur_ty]};
-    CK(cudaMemsetAsync(s->cell_count, 0, sizeof(uint32_t) * s->grid.cells, s->stream));
-    key_count_kernel<false><<<div_up(n, tb), tb, 0, s->stream>>>(src, n, s->grid, s->cell_count, s->rank);
-    s->launches += 1;
-    int rc = enqueue_scan(s);
-    if (rc) return rc;
-    scatter_kernel<false><<<div_up(n, tb), tb, 0, s->stream>>>(src, n, s->grid, s->cell_start, s->rank, s->perm);
-    gather_kernel<false><<<div_up(n, tb), tb, 0, s->stream>>>(src, n, s->grid, s->cell_start, s->perm,
-                                                              s->pos[s->cur_pos ^ 1], s->vel[s->cur_vel ^ 1],
-                                                              s->ty[s->cur_ty ^ 1], s->cell_id);
-    s->launches += 2;
-    CK(cudaGetLastError());
-    s->cur_pos ^= 1;
-    s->cur_vel ^= 1;
-    s->cur_ty ^= 1;
-    rc = enqueue_tiles(s);
-    if (rc) return rc;
-    s->rebins_executed += 1;
+// Bin all slabs of the team: an ingested frame (`ingest`: `records`/`count` in device memory), or the
+// live state (bucket_move, kernel_bucket.cuh:5-39) including migration between slabs.
+int team_bin(const Team& t, bool ingest, const Particle* records, uint32_t count) {
+    const bool slabs = t.ranks[0]->nranks > 1;
+    std::vector<XferOp> ops(t.count);
+    int rc;
+    for (int r = 0; r < t.count; ++r) {
+        PsimStepper* s = t.ranks[r];
+        CK(cudaMemsetAsync(s->d_flags, 0, sizeof(uint32_t), s->stream));
+    }
+    if (!ingest && slabs) {
+        for (int r = 0; r < t.count; ++r)
+            if ((rc = bin_phase_migrants(t.ranks[r], ops[r]))) return rc;
+        if ((rc = team_exchange(t, ops))) return rc;
+    }
+    ops.assign(t.count, XferOp());
+    for (int r = 0; r < t.count; ++r) {
+        PsimStepper* s = t.ranks[r];
+        Source src{};
+        if (ingest) {
+            src.aos_lo = records;
+            src.n_lo = count;
+            src.strict = 0;
+        } else {
+            src.pos = s->pos[s->cur_pos];
+            src.vel = s->vel[s->cur_vel];
+            src.ty = s->ty[s->cur_ty];
+            src.soa_lo = s->own_lo;
+            src.n_soa = s->n;
+            src.strict = 1;
+            if (has_lower(s)) {
+                src.aos_lo = reinterpret_cast<const Particle*>(s->inbox[0] + sizeof(MigrantBoxHeader));
+                src.n_lo = s->box_capacity;
+            }
+            if (has_upper(s)) {
+                src.aos_hi = reinterpret_cast<const Particle*>(s->inbox[1] + sizeof(MigrantBoxHeader));
+                src.n_hi = s->box_capacity;
+            }
+        }
+        if ((rc = bin_phase_count(s, src, ops[r]))) return rc;
+    }
+    if ((rc = team_exchange(t, ops))) return rc;
+    const bool need_counts = ingest || slabs;
+    for (int r = 0; r < t.count; ++r)
+        if ((rc = bin_phase_scan(t.ranks[r], need_counts))) return rc;
+    if (need_counts) {
+        int first_error = PSIM_OK;
+        for (int r = 0; r < t.count; ++r) {
+            rc = bin_phase_commit(t.ranks[r]);
+            if (rc && !first_error) {
+                first_error = rc;
+                if (t.group) t.group->error = t.ranks[r]->error;
+            }
+        }
+        if (first_error) return first_error;
+    }
+    ops.assign(t.count, XferOp());
+    for (int r = 0; r < t.count; ++r)
+        if ((rc = bin_phase_place(t.ranks[r], ingest, ops[r]))) return rc;
+    if ((rc = team_exchange(t, ops))) return rc;
+    for (int r = 0; r < t.count; ++r) {
+        if ((rc = bin_phase_tiles(t.ranks[r]))) return rc;
+        if (!ingest) t.ranks[r]->rebins_executed += 1;
+    }
     return PSIM_OK;
 }
+
+// ------------------------------------------------------------------------------------------------
+// Steps, snapshots, frames
+// ------------------------------------------------------------------------------------------------
 
 int enqueue_step(PsimStepper* s) {
     if (s->n == 0) {
+        s->cur_pos ^= 1;  // ghost rows are exchanged into the buffer the next step reads
         s->steps_executed += 1;
         return PSIM_OK;
     }
@@ -905,7 +1381,8 @@ int enqueue_step(PsimStepper* s) {
     a.cell_id = s->cell_id;
     a.cell_start = s->cell_start;
     a.tiles = s->tiles;
-    a.n = s->n;
+    a.own_lo = s->own_lo;
+    a.own_hi = s->own_hi;
     a.g = s->grid;
     a.ph = s->phys;
     uint32_t tiles = div_up(s->n, kTile);
@@ -931,12 +1408,26 @@ int enqueue_step(PsimStepper* s) {
     return PSIM_OK;
 }
 
+// One leapfrog step of every slab, then the halo exchange: each slab's new boundary-row positions
+// become its neighbours' ghost rows for the next step.
+int team_step(const Team& t) {
+    int rc;
+    for (int r = 0; r < t.count; ++r) {
+        if ((rc = enqueue_step(t.ranks[r]))) return rc;
+        t.ranks[r]->fresh_scene = false;
+    }
+    if (t.ranks[0]->nranks == 1) return PSIM_OK;
+    std::vector<XferOp> ops(t.count);
+    for (int r = 0; r < t.count; ++r) ops[r] = ghost_positions_op(t.ranks[r]);
+    return team_exchange(t, ops);
+}
+
 int enqueue_snapshot(PsimStepper* s) {
     // the previous snapshot must have left the staging buffer before it is overwritten
     CK(cudaStreamWaitEvent(s->stream, s->snapshot_consumed, 0));
     if (s->n) {
         pack_kernel<<<div_up(s->n, 256), 256, 0, s->stream>>>(s->pos[s->cur_pos], s->vel[s->cur_vel], s->ty[s->cur_ty],
-                                                              s->n, s->staging);
+                                                              s->own_lo, s->own_hi, s->snapshot);
         s->launches += 1;
         CK(cudaGetLastError());
     }
@@ -944,6 +1435,13 @@ int enqueue_snapshot(PsimStepper* s) {
     s->snapshot_n = s->n;
     s->snapshot_meta = s->meta;
     s->has_snapshot = true;
+    return PSIM_OK;
+}
+
+int team_snapshot(const Team& t) {
+    int rc;
+    for (int r = 0; r < t.count; ++r)
+        if ((rc = enqueue_snapshot(t.ranks[r]))) return rc;
     return PSIM_OK;
 }
 
@@ -958,40 +1456,95 @@ int collect_timing(PsimStepper* s) {
     return PSIM_OK;
 }
 
-// Bin `count` wire-format records that sit in s->staging (device).
-int ingest_staged(PsimStepper* s, uint32_t count) {
-    const uint32_t tb = 256;
-    Source src{s->staging, nullptr, nullptr, nullptr};
-    CK(cudaMemsetAsync(s->cell_count, 0, sizeof(uint32_t) * s->grid.cells, s->stream));
-    if (count) {
-        key_count_kernel<true><<<div_up(count, tb), tb, 0, s->stream>>>(src, count, s->grid, s->cell_count, s->rank);
-        s->launches += 1;
+// Bin `count` wire-format records that sit in device memory at `records`, on every slab of the team.
+int team_ingest(const Team& t, const Particle* records, uint32_t count) {
+    int rc = team_bin(t, true, records, count);
+    if (rc) return rc;
+    for (int r = 0; r < t.count; ++r) {
+        PsimStepper* s = t.ranks[r];
+        s->has_scene = true;
+        s->native_countdown = 0;
+        s->fresh_scene = true;
     }
-    int rc = enqueue_scan(s);
-    if (rc) return rc;
-    CK(cudaMemcpyAsync(s->h_total, s->cell_start + s->grid.cells, sizeof(uint32_t), cudaMemcpyDeviceToHost,
-                       s->stream));
-    CK(cudaStreamSynchronize(s->stream));
-    uint32_t live = *s->h_total;
-    if (live > s->cfg.max_particles)
-        return fail(s, PSIM_ECAPACITY, "%u live particles exceed max_particles = %u", live, s->cfg.max_particles);
-    s->n = live;
-    s->cur_pos = s->cur_vel = s->cur_ty = 0;
-    if (live) {
-        scatter_kernel<true><<<div_up(count, tb), tb, 0, s->stream>>>(src, count, s->grid, s->cell_start, s->rank,
-                                                                      s->perm);
-        gather_kernel<true><<<div_up(live, tb), tb, 0, s->stream>>>(src, live, s->grid, s->cell_start, s->perm,
-                                                                    s->pos[0], s->vel[0], s->ty[0], s->cell_id);
-        s->launches += 2;
-        CK(cudaGetLastError());
+    // the ingested scene itself can be downloaded (cuda_simulator.cu:28-31)
+    if ((rc = team_snapshot(t))) return rc;
+    for (int r = 0; r < t.count; ++r) {
+        PsimStepper* s = t.ranks[r];
+        CK(cudaStreamSynchronize(s->stream));
     }
-    rc = enqueue_tiles(s);
-    if (rc) return rc;
-    s->has_scene = true;
-    s->native_countdown = 0;
-    rc = enqueue_snapshot(s);  // the ingested scene itself can be downloaded (cuda_simulator.cu:28-31)
-    if (rc) return rc;
-    CK(cudaStreamSynchronize(s->stream));
+    return PSIM_OK;
+}
+
+// One frame (Kernel::run_async for MatrixBuckets): steps_per_frame steps with re-binning on the
+// configured schedule, then a snapshot. All slabs of a team share metadata and schedule state.
+int team_run_frame(const Team& t) {
+    PsimStepper* lead = t.ranks[0];
+    const uint32_t target = lead->meta.steps_per_frame;
+    int rc;
+    if (lead->cfg.schedule == PSIM_SCHEDULE_REFERENCE) {
+        // bucket_kernel_run_async, kernel_bucket.cuh:181-206: the reference always runs one step,
+        // then alternates "re-bin + 1 step" with pairs of steps, 16 steps between re-bins counted
+        // from the first re-bin, the countdown restarting with every frame. Pairs make it overshoot
+        // an odd remainder by one step.
+        const int move_every_n = 16;
+        int countdown = 0;
+        uint32_t steps = 0;
+        if ((rc = team_step(t))) return rc;
+        steps += 1;
+        while (steps < target) {
+            if (countdown <= 0) {
+                if ((rc = team_bin(t, false, nullptr, 0))) return rc;
+                countdown = move_every_n;
+                if ((rc = team_step(t))) return rc;
+                countdown -= 1;
+                steps += 1;
+            } else {
+                if ((rc = team_step(t))) return rc;
+                if ((rc = team_step(t))) return rc;
+                countdown -= 2;
+                steps += 2;
+            }
+        }
+    } else {
+        for (uint32_t k = 0; k < target; ++k) {
+            if (lead->native_countdown <= 0) {
+                if (!lead->fresh_scene)  // a freshly ingested scene is already binned
+                    if ((rc = team_bin(t, false, nullptr, 0))) return rc;
+                lead->native_countdown = (int)lead->cfg.rebin_every;
+            }
+            if ((rc = team_step(t))) return rc;
+            lead->native_countdown -= 1;
+        }
+    }
+    for (int r = 0; r < t.count; ++r) t.ranks[r]->native_countdown = lead->native_countdown;
+    return team_snapshot(t);
+}
+
+Team lone(PsimStepper* const* s) { return Team{s, 1, nullptr}; }
+
+int check_lone(PsimStepper* s, const char* what) {
+    if (s->group) return fail(s, PSIM_ESTATE, "%s: this stepper is a slab of a group; use the psim_group_* call", what);
+    return PSIM_OK;
+}
+
+void write_header(FrameHeader* dst, const FrameMetadata& meta, uint32_t count) {
+    // FrameHeader::new (particle.rs:214-223)
+    static const uint8_t sig0[4] = {0x36, 0xbc, 0xe9, 0xbd}, sig1[4] = {0xac, 0xc4, 0x12, 0xec};
+    std::memcpy(dst->signature_start, sig0, 4);
+    std::memcpy(dst->signature_end, sig1, 4);
+    dst->_padding = 0;
+    dst->metadata = meta;
+    dst->particle_count = count;
+}
+
+// Copy this slab's packed snapshot to `out` (host); waits only for the snapshot.
+int download_records(PsimStepper* s, Particle* out) {
+    CK(cudaStreamWaitEvent(s->copy_stream, s->snapshot_ready, 0));
+    if (s->snapshot_n)
+        CK(cudaMemcpyAsync(out, s->snapshot, sizeof(Particle) * (size_t)s->snapshot_n, cudaMemcpyDeviceToHost,
+                           s->copy_stream));
+    CK(cudaEventRecord(s->snapshot_consumed, s->copy_stream));
+    CK(cudaStreamSynchronize(s->copy_stream));
     return PSIM_OK;
 }
 
@@ -1009,6 +1562,8 @@ PsimConfig psim_default_config(void) {
     c.rebin_every = 0;
     c.device = -1;
     c.use_graph = 0;
+    c.slab_rank = 0;
+    c.slab_count = 1;
     return c;
 }
 
@@ -1019,6 +1574,7 @@ void psim_destroy(PsimStepper* s) {
     cudaSetDevice(s->device);
     if (s->stream) cudaStreamSynchronize(s->stream);
     if (s->copy_stream) cudaStreamSynchronize(s->copy_stream);
+    if (s->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(s->comm);
     for (auto& ev : s->timing_events) {
         cudaEventDestroy(ev.first);
         cudaEventDestroy(ev.second);
@@ -1027,16 +1583,23 @@ void psim_destroy(PsimStepper* s) {
         cudaFree(s->pos[k]);
         cudaFree(s->vel[k]);
         cudaFree(s->ty[k]);
+        cudaFree(s->outbox[k]);
+        cudaFree(s->inbox[k]);
+        cudaFree(s->mig_idx[k]);
     }
     cudaFree(s->cell_start);
     cudaFree(s->cell_count);
     cudaFree(s->block_sum);
-    cudaFree(s->rank);
+    cudaFree(s->rank_in_cell);
     cudaFree(s->perm);
     cudaFree(s->cell_id);
     cudaFree(s->tiles);
     cudaFree(s->staging);
-    if (s->h_total) cudaFreeHost(s->h_total);
+    cudaFree(s->snapshot);
+    cudaFree(s->mig_counters);
+    cudaFree(s->d_flags);
+    cudaFree(s->d_counts);
+    if (s->h_counts) cudaFreeHost(s->h_counts);
     if (s->snapshot_ready) cudaEventDestroy(s->snapshot_ready);
     if (s->snapshot_consumed) cudaEventDestroy(s->snapshot_consumed);
     if (s->own_stream) cudaStreamDestroy(s->own_stream);
@@ -1057,6 +1620,12 @@ int psim_create(const PsimConfig* config, PsimStepper** out) {
     if (config->max_particles == 0 || config->max_particles > 0x7FFFFF00u)
         return fail(s, PSIM_EINVAL, "psim_create: max_particles out of range");
     if (config->schedule > PSIM_SCHEDULE_NATIVE) return fail(s, PSIM_EINVAL, "psim_create: unknown schedule");
+    const uint32_t nranks = config->slab_count ? config->slab_count : 1;
+    const uint32_t rows_global = 1u << config->grid_y_log2;
+    if (config->slab_rank >= nranks) return fail(s, PSIM_EINVAL, "psim_create: slab_rank %u of %u", config->slab_rank, nranks);
+    if (rows_global % nranks != 0 || rows_global / nranks < 2)
+        return fail(s, PSIM_EINVAL, "psim_create: %u cell rows do not split into %u slabs of at least 2 rows", rows_global,
+                    nranks);
 
     int device = config->device;
     int ndev = 0;
@@ -1075,16 +1644,36 @@ int psim_create(const PsimConfig* config, PsimStepper** out) {
 
     PsimStepper* st = new PsimStepper;
     st->cfg = *config;
+    st->cfg.slab_count = nranks;
     if (st->cfg.rebin_every == 0) st->cfg.rebin_every = 17;
     st->device = device;
+    st->rank = (int)config->slab_rank;
+    st->nranks = (int)nranks;
     Grid& g = st->grid;
     g.lx = config->grid_x_log2;
-    g.ly = config->grid_y_log2;
     g.bx = 1u << g.lx;
-    g.by = 1u << g.ly;
-    g.cells = g.bx * g.by;
     g.sx = 32 - g.lx;
-    g.sy = 32 - g.ly;
+    g.sy = 32 - config->grid_y_log2;
+    g.own_rows = rows_global / nranks;
+    g.own_row0 = st->rank > 0 ? 1 : 0;
+    g.by = g.own_rows + g.own_row0 + (st->rank + 1 < st->nranks ? 1 : 0);
+    g.row_offset = (int32_t)(st->rank * g.own_rows) - (int32_t)g.own_row0;
+    g.cells = g.bx * g.by;
+
+    const size_t cap = config->max_particles;
+    if (nranks > 1) {
+        // a ghost row holds one cell row of a neighbour: by default as many particles as this slab's rows
+        // hold on average, times 4, and at least 4096
+        uint32_t dflt = (uint32_t)std::min<size_t>(cap, std::max<size_t>(4096, 4 * (cap / g.own_rows + 1)));
+        st->ghost_cap = config->ghost_capacity ? config->ghost_capacity : dflt;
+        st->box_capacity = config->migrant_capacity ? config->migrant_capacity : dflt;
+    }
+    st->cap_total = (uint32_t)std::min<size_t>(cap + 2 * (size_t)st->ghost_cap, 0x7FFFFF00u);
+    st->box_bytes = sizeof(MigrantBoxHeader) + sizeof(Particle) * (size_t)st->box_capacity;
+    st->ingest_cap = std::max<uint32_t>(config->ingest_capacity, config->max_particles);
+    const size_t cap_total = st->cap_total;
+    const size_t cand_cap = std::max<size_t>(st->ingest_cap, cap_total + 2 * (size_t)st->box_capacity);
+
     s = st;  // from here on failures are recorded on the object (and it is destroyed before returning)
 #define CKC(call)                                                                                        \
     do {                                                                                                 \
@@ -1096,28 +1685,37 @@ int psim_create(const PsimConfig* config, PsimStepper** out) {
             return PSIM_ECUDA;                                                                           \
         }                                                                                                \
     } while (0)
-    const size_t cap = config->max_particles;
     CKC(cudaStreamCreateWithFlags(&st->own_stream, cudaStreamNonBlocking));
     CKC(cudaStreamCreateWithFlags(&st->copy_stream, cudaStreamNonBlocking));
     st->stream = st->own_stream;
     CKC(cudaEventCreateWithFlags(&st->snapshot_ready, cudaEventDisableTiming));
     CKC(cudaEventCreateWithFlags(&st->snapshot_consumed, cudaEventDisableTiming));
     for (int k = 0; k < 2; ++k) {
-        CKC(cudaMalloc(&st->pos[k], sizeof(uint2) * (cap + kPadParticles)));
-        CKC(cudaMemset(st->pos[k], 0, sizeof(uint2) * (cap + kPadParticles)));
-        CKC(cudaMalloc(&st->vel[k], sizeof(float2) * cap));
-        CKC(cudaMalloc(&st->ty[k], sizeof(int32_t) * cap));
+        CKC(cudaMalloc(&st->pos[k], sizeof(uint2) * (cap_total + kPadParticles)));
+        CKC(cudaMemset(st->pos[k], 0, sizeof(uint2) * (cap_total + kPadParticles)));
+        CKC(cudaMalloc(&st->vel[k], sizeof(float2) * cap_total));
+        CKC(cudaMalloc(&st->ty[k], sizeof(int32_t) * cap_total));
+        if (nranks > 1) {
+            CKC(cudaMalloc(&st->outbox[k], st->box_bytes));
+            CKC(cudaMalloc(&st->inbox[k], st->box_bytes));
+            CKC(cudaMalloc(&st->mig_idx[k], sizeof(uint32_t) * (size_t)st->box_capacity));
+        }
     }
     CKC(cudaMalloc(&st->cell_start, sizeof(uint32_t) * ((size_t)g.cells + 1 + kPadCells)));
     CKC(cudaMalloc(&st->cell_count, sizeof(uint32_t) * (size_t)g.cells));
     CKC(cudaMalloc(&st->block_sum, sizeof(uint32_t) * (size_t)div_up(g.cells, kScanBlock)));
-    CKC(cudaMalloc(&st->rank, sizeof(uint32_t) * cap));
-    CKC(cudaMalloc(&st->perm, sizeof(uint32_t) * cap));
-    CKC(cudaMalloc(&st->cell_id, sizeof(uint32_t) * cap));
-    CKC(cudaMalloc(&st->tiles, sizeof(TileDesc) * (size_t)div_up((uint32_t)cap, kTile)));
-    CKC(cudaMalloc(&st->staging, sizeof(Particle) * cap));
-    CKC(cudaMallocHost(&st->h_total, sizeof(uint32_t)));
+    CKC(cudaMalloc(&st->rank_in_cell, sizeof(uint32_t) * cand_cap));
+    CKC(cudaMalloc(&st->perm, sizeof(uint32_t) * cap_total));
+    CKC(cudaMalloc(&st->cell_id, sizeof(uint32_t) * cap_total));
+    CKC(cudaMalloc(&st->tiles, sizeof(TileDesc) * ((size_t)div_up((uint32_t)cap, kTile) + 1)));
+    CKC(cudaMalloc(&st->staging, sizeof(Particle) * (size_t)st->ingest_cap));
+    CKC(cudaMalloc(&st->snapshot, sizeof(Particle) * cap));
+    CKC(cudaMalloc(&st->mig_counters, 2 * sizeof(uint32_t)));
+    CKC(cudaMalloc(&st->d_flags, sizeof(uint32_t)));
+    CKC(cudaMalloc(&st->d_counts, 8 * sizeof(uint32_t)));
+    CKC(cudaMallocHost(&st->h_counts, 16 * sizeof(uint32_t)));
     CKC(cudaMemset(st->cell_start, 0, sizeof(uint32_t) * ((size_t)g.cells + 1 + kPadCells)));
+    CKC(cudaMemset(st->d_flags, 0, sizeof(uint32_t)));
 #undef CKC
     *out = st;
     return PSIM_OK;
@@ -1125,39 +1723,69 @@ int psim_create(const PsimConfig* config, PsimStepper** out) {
 
 int psim_set_stream(PsimStepper* s, void* cuda_stream) {
     if (!s) return PSIM_EINVAL;
+    int rc = check_lone(s, "psim_set_stream");
+    if (rc) return rc;
     CK(cudaSetDevice(s->device));
     CK(cudaStreamSynchronize(s->stream));
     s->stream = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : s->own_stream;
     return PSIM_OK;
 }
 
+int psim_comm_unique_id(void* out128) {
+    PsimStepper* s = nullptr;
+    if (!out128) return fail(s, PSIM_EINVAL, "psim_comm_unique_id: null argument");
+    if (!load_nccl(nullptr)) return PSIM_ENCCL;
+    ncclUniqueId id;
+    CKN(g_nccl.GetUniqueId(&id));
+    std::memcpy(out128, &id, sizeof id);
+    return PSIM_OK;
+}
+
+int psim_comm_init(PsimStepper* s, const void* unique_id128) {
+    if (!s || !unique_id128) return PSIM_EINVAL;
+    int rc = check_lone(s, "psim_comm_init");
+    if (rc) return rc;
+    if (s->nranks == 1) return PSIM_OK;  // a single slab never communicates
+    if (s->comm) return fail(s, PSIM_ESTATE, "psim_comm_init: already initialised");
+    if (!load_nccl(s)) return PSIM_ENCCL;
+    CK(cudaSetDevice(s->device));
+    ncclUniqueId id;
+    std::memcpy(&id, unique_id128, sizeof id);
+    CKN(g_nccl.CommInitRank(&s->comm, s->nranks, id, s->rank));
+    return PSIM_OK;
+}
+
 int psim_upload_frame(PsimStepper* s, const FrameHeader* frame) {
     if (!s || !frame) return PSIM_EINVAL;
+    int rc = check_lone(s, "psim_upload_frame");
+    if (rc) return rc;
     CK(cudaSetDevice(s->device));
-    if (frame->particle_count > s->cfg.max_particles)
-        return fail(s, PSIM_ECAPACITY, "frame holds %u particles, max_particles = %u", frame->particle_count,
-                    s->cfg.max_particles);
+    if (frame->particle_count > s->ingest_cap)
+        return fail(s, PSIM_ECAPACITY, "frame holds %u particles, the ingest buffer %u (max_particles / ingest_capacity)",
+                    frame->particle_count, s->ingest_cap);
     CK(cudaStreamSynchronize(s->stream));
     CK(cudaStreamSynchronize(s->copy_stream));
     apply_metadata(s, frame->metadata);
     if (frame->particle_count)
         CK(cudaMemcpyAsync(s->staging, frame->particles, sizeof(Particle) * (size_t)frame->particle_count,
                            cudaMemcpyHostToDevice, s->stream));
-    return ingest_staged(s, frame->particle_count);
+    return team_ingest(lone(&s), s->staging, frame->particle_count);
 }
 
 int psim_upload_device(PsimStepper* s, const FrameMetadata* meta, const void* d_particles, uint32_t count) {
     if (!s || !meta || (count && !d_particles)) return PSIM_EINVAL;
+    int rc = check_lone(s, "psim_upload_device");
+    if (rc) return rc;
     CK(cudaSetDevice(s->device));
-    if (count > s->cfg.max_particles)
-        return fail(s, PSIM_ECAPACITY, "%u particles, max_particles = %u", count, s->cfg.max_particles);
+    if (count > s->ingest_cap)
+        return fail(s, PSIM_ECAPACITY, "%u particles, the ingest buffer holds %u", count, s->ingest_cap);
     CK(cudaStreamSynchronize(s->stream));
     CK(cudaStreamSynchronize(s->copy_stream));
     apply_metadata(s, *meta);
     if (count)
         CK(cudaMemcpyAsync(s->staging, d_particles, sizeof(Particle) * (size_t)count, cudaMemcpyDeviceToDevice,
                            s->stream));
-    return ingest_staged(s, count);
+    return team_ingest(lone(&s), s->staging, count);
 }
 
 int psim_set_metadata(PsimStepper* s, const FrameMetadata* meta) {
@@ -1174,20 +1802,25 @@ int psim_get_metadata(const PsimStepper* s, FrameMetadata* out) {
 
 int psim_step_async(PsimStepper* s, uint32_t steps) {
     if (!s) return PSIM_EINVAL;
+    int rc = check_lone(s, "psim_step_async");
+    if (rc) return rc;
     if (!s->has_scene) return fail(s, PSIM_ESTATE, "psim_step_async: no scene uploaded");
     CK(cudaSetDevice(s->device));
     for (uint32_t k = 0; k < steps; ++k) {
-        int rc = enqueue_step(s);
-        if (rc) return rc;
+        if ((rc = team_step(lone(&s)))) return rc;
+        s->fresh_scene = false;
     }
     return PSIM_OK;
 }
 
 int psim_rebin_async(PsimStepper* s) {
     if (!s) return PSIM_EINVAL;
+    int rc = check_lone(s, "psim_rebin_async");
+    if (rc) return rc;
     if (!s->has_scene) return fail(s, PSIM_ESTATE, "psim_rebin_async: no scene uploaded");
     CK(cudaSetDevice(s->device));
-    return enqueue_rebin(s);
+    s->fresh_scene = false;
+    return team_bin(lone(&s), false, nullptr, 0);
 }
 
 int psim_snapshot_async(PsimStepper* s) {
@@ -1199,48 +1832,13 @@ int psim_snapshot_async(PsimStepper* s) {
 
 int psim_run_frame_async(PsimStepper* s) {
     if (!s) return PSIM_EINVAL;
+    int rc = check_lone(s, "psim_run_frame_async");
+    if (rc) return rc;
     if (!s->has_scene) return fail(s, PSIM_ESTATE, "psim_run_frame_async: no scene uploaded");
     CK(cudaSetDevice(s->device));
-    const uint32_t target = s->meta.steps_per_frame;
-    int rc;
-    if (s->cfg.schedule == PSIM_SCHEDULE_REFERENCE) {
-        // bucket_kernel_run_async, kernel_bucket.cuh:181-206: the reference always runs one step,
-        // then alternates "re-bin + 1 step" with pairs of steps, 16 steps between re-bins counted
-        // from the first re-bin, the countdown restarting with every frame. Pairs make it overshoot
-        // an odd remainder by one step.
-        const int move_every_n = 16;
-        int countdown = 0;
-        uint32_t steps = 0;
-        if ((rc = enqueue_step(s))) return rc;
-        steps += 1;
-        while (steps < target) {
-            if (countdown <= 0) {
-                if ((rc = enqueue_rebin(s))) return rc;
-                countdown = move_every_n;
-                if ((rc = enqueue_step(s))) return rc;
-                countdown -= 1;
-                steps += 1;
-            } else {
-                if ((rc = enqueue_step(s))) return rc;
-                if ((rc = enqueue_step(s))) return rc;
-                countdown -= 2;
-                steps += 2;
-            }
-        }
-    } else {
-        for (uint32_t k = 0; k < target; ++k) {
-            if (s->native_countdown <= 0) {
-                // a freshly ingested scene is already binned
-                if (s->steps_executed != 0 || s->rebins_executed != 0 || k != 0) {
-                    if ((rc = enqueue_rebin(s))) return rc;
-                }
-                s->native_countdown = (int)s->cfg.rebin_every;
-            }
-            if ((rc = enqueue_step(s))) return rc;
-            s->native_countdown -= 1;
-        }
-    }
-    return enqueue_snapshot(s);
+    rc = team_run_frame(lone(&s));
+    s->fresh_scene = false;
+    return rc;
 }
 
 int psim_sync(PsimStepper* s) {
@@ -1258,19 +1856,9 @@ int psim_download_frame(PsimStepper* s, FrameHeader* dst) {
     if (dst->particle_count < s->snapshot_n)
         return fail(s, PSIM_ECAPACITY, "psim_download_frame: destination holds %u particles, snapshot has %u",
                     dst->particle_count, s->snapshot_n);
-    CK(cudaStreamWaitEvent(s->copy_stream, s->snapshot_ready, 0));
-    if (s->snapshot_n)
-        CK(cudaMemcpyAsync(dst->particles, s->staging, sizeof(Particle) * (size_t)s->snapshot_n,
-                           cudaMemcpyDeviceToHost, s->copy_stream));
-    CK(cudaEventRecord(s->snapshot_consumed, s->copy_stream));
-    CK(cudaStreamSynchronize(s->copy_stream));
-    // FrameHeader::new (particle.rs:214-223)
-    static const uint8_t sig0[4] = {0x36, 0xbc, 0xe9, 0xbd}, sig1[4] = {0xac, 0xc4, 0x12, 0xec};
-    std::memcpy(dst->signature_start, sig0, 4);
-    std::memcpy(dst->signature_end, sig1, 4);
-    dst->_padding = 0;
-    dst->metadata = s->snapshot_meta;
-    dst->particle_count = s->snapshot_n;
+    int rc = download_records(s, dst->particles);
+    if (rc) return rc;
+    write_header(dst, s->snapshot_meta, s->snapshot_n);
     return PSIM_OK;
 }
 
@@ -1313,10 +1901,196 @@ int psim_get_step_timing(PsimStepper* s, double* total_ms, uint64_t* launches) {
 
 int psim_device_state(PsimStepper* s, const void** pos, const void** vel, const void** ty, const void** cell_start) {
     if (!s) return PSIM_EINVAL;
-    if (pos) *pos = s->pos[s->cur_pos];
-    if (vel) *vel = s->vel[s->cur_vel];
-    if (ty) *ty = s->ty[s->cur_ty];
+    if (pos) *pos = s->pos[s->cur_pos] + s->own_lo;
+    if (vel) *vel = s->vel[s->cur_vel] + s->own_lo;
+    if (ty) *ty = s->ty[s->cur_ty] + s->own_lo;
     if (cell_start) *cell_start = s->cell_start;
+    return PSIM_OK;
+}
+
+int psim_slab_info(const PsimStepper* s, PsimSlabInfo* out) {
+    if (!s || !out) return PSIM_EINVAL;
+    std::memset(out, 0, sizeof *out);
+    out->slab_rank = (uint32_t)s->rank;
+    out->slab_count = (uint32_t)s->nranks;
+    out->first_row = (uint32_t)(s->rank * (int)s->grid.own_rows);
+    out->rows = s->grid.own_rows;
+    out->local_rows = s->grid.by;
+    out->first_local_row = (uint32_t)((int32_t)out->first_row - (int32_t)s->grid.own_row0);
+    out->particles = s->n;
+    out->ghost_below = s->own_lo;
+    out->ghost_above = s->n_total - s->own_hi;
+    out->ghost_capacity = s->ghost_cap;
+    out->migrant_capacity = s->box_capacity;
+    return PSIM_OK;
+}
+
+// ---- slabs of one process on one device ---------------------------------------------------------
+
+const char* psim_group_last_error(const PsimGroup* g) { return g ? g->error.c_str() : g_create_error.c_str(); }
+
+int psim_group_create(PsimStepper* const* steppers, uint32_t count, PsimGroup** out) {
+    PsimStepper* s = nullptr;
+    if (!steppers || !out || count == 0) return fail(s, PSIM_EINVAL, "psim_group_create: bad argument");
+    *out = nullptr;
+    for (uint32_t r = 0; r < count; ++r) {
+        PsimStepper* m = steppers[r];
+        if (!m || m->group || m->comm || m->nranks != (int)count || m->rank != (int)r ||
+            m->device != steppers[0]->device || m->cfg.grid_x_log2 != steppers[0]->cfg.grid_x_log2 ||
+            m->cfg.grid_y_log2 != steppers[0]->cfg.grid_y_log2 || m->cfg.schedule != steppers[0]->cfg.schedule ||
+            m->cfg.rebin_every != steppers[0]->cfg.rebin_every || m->box_capacity != steppers[0]->box_capacity)
+            return fail(s, PSIM_EINVAL, "psim_group_create: stepper %u must be slab %u of %u on the group's device "
+                        "with the group's grid, schedule and capacities", r, r, count);
+    }
+    CK(cudaSetDevice(steppers[0]->device));
+    PsimGroup* g = new PsimGroup;
+    g->ranks.assign(steppers, steppers + count);
+    g->stream = steppers[0]->own_stream;
+    for (PsimStepper* m : g->ranks) {
+        cudaStreamSynchronize(m->stream);
+        m->group = g;
+        m->stream = g->stream;
+    }
+    *out = g;
+    return PSIM_OK;
+}
+
+void psim_group_destroy(PsimGroup* g) {
+    if (!g) return;
+    for (PsimStepper* m : g->ranks) {
+        cudaStreamSynchronize(g->stream);
+        m->group = nullptr;
+        m->stream = m->own_stream;
+    }
+    delete g;
+}
+
+}  // extern "C"
+
+namespace {
+Team team_of(PsimGroup* g) { return Team{g->ranks.data(), (int)g->ranks.size(), g}; }
+
+int group_fail(PsimGroup* g, int rc) {
+    if (rc && g->error.empty())
+        for (PsimStepper* m : g->ranks)
+            if (!m->error.empty()) g->error = m->error;
+    return rc;
+}
+}  // namespace
+
+extern "C" {
+
+int psim_group_upload_frame(PsimGroup* g, const FrameHeader* frame) {
+    if (!g || !frame) return PSIM_EINVAL;
+    g->error.clear();
+    PsimStepper* s = g->ranks[0];
+    for (PsimStepper* m : g->ranks) m->error.clear();
+    CK(cudaSetDevice(s->device));
+    if (frame->particle_count > s->ingest_cap)
+        return group_fail(g, fail(s, PSIM_ECAPACITY, "frame holds %u particles, the ingest buffer of slab 0 holds %u",
+                                  frame->particle_count, s->ingest_cap));
+    CK(cudaStreamSynchronize(g->stream));
+    for (PsimStepper* m : g->ranks) {
+        CK(cudaStreamSynchronize(m->copy_stream));
+        apply_metadata(m, frame->metadata);
+    }
+    if (frame->particle_count)
+        CK(cudaMemcpyAsync(s->staging, frame->particles, sizeof(Particle) * (size_t)frame->particle_count,
+                           cudaMemcpyHostToDevice, g->stream));
+    return group_fail(g, team_ingest(team_of(g), s->staging, frame->particle_count));
+}
+
+int psim_group_set_metadata(PsimGroup* g, const FrameMetadata* meta) {
+    if (!g || !meta) return PSIM_EINVAL;
+    for (PsimStepper* m : g->ranks) apply_metadata(m, *meta);
+    return PSIM_OK;
+}
+
+int psim_group_step_async(PsimGroup* g, uint32_t steps) {
+    if (!g) return PSIM_EINVAL;
+    g->error.clear();
+    PsimStepper* s = g->ranks[0];
+    if (!s->has_scene) return group_fail(g, fail(s, PSIM_ESTATE, "psim_group_step_async: no scene uploaded"));
+    CK(cudaSetDevice(s->device));
+    for (uint32_t k = 0; k < steps; ++k) {
+        int rc = team_step(team_of(g));
+        if (rc) return group_fail(g, rc);
+        for (PsimStepper* m : g->ranks) m->fresh_scene = false;
+    }
+    return PSIM_OK;
+}
+
+int psim_group_rebin_async(PsimGroup* g) {
+    if (!g) return PSIM_EINVAL;
+    g->error.clear();
+    PsimStepper* s = g->ranks[0];
+    if (!s->has_scene) return group_fail(g, fail(s, PSIM_ESTATE, "psim_group_rebin_async: no scene uploaded"));
+    CK(cudaSetDevice(s->device));
+    for (PsimStepper* m : g->ranks) m->fresh_scene = false;
+    return group_fail(g, team_bin(team_of(g), false, nullptr, 0));
+}
+
+int psim_group_snapshot_async(PsimGroup* g) {
+    if (!g) return PSIM_EINVAL;
+    g->error.clear();
+    PsimStepper* s = g->ranks[0];
+    if (!s->has_scene) return group_fail(g, fail(s, PSIM_ESTATE, "psim_group_snapshot_async: no scene uploaded"));
+    CK(cudaSetDevice(s->device));
+    return group_fail(g, team_snapshot(team_of(g)));
+}
+
+int psim_group_run_frame_async(PsimGroup* g) {
+    if (!g) return PSIM_EINVAL;
+    g->error.clear();
+    PsimStepper* s = g->ranks[0];
+    if (!s->has_scene) return group_fail(g, fail(s, PSIM_ESTATE, "psim_group_run_frame_async: no scene uploaded"));
+    CK(cudaSetDevice(s->device));
+    int rc = team_run_frame(team_of(g));
+    for (PsimStepper* m : g->ranks) m->fresh_scene = false;
+    return group_fail(g, rc);
+}
+
+int psim_group_sync(PsimGroup* g) {
+    if (!g) return PSIM_EINVAL;
+    PsimStepper* s = g->ranks[0];
+    CK(cudaSetDevice(s->device));
+    CK(cudaStreamSynchronize(g->stream));
+    for (PsimStepper* m : g->ranks)
+        if (m->timing) {
+            int rc = collect_timing(m);
+            if (rc) return rc;
+        }
+    return PSIM_OK;
+}
+
+uint32_t psim_group_particle_count(const PsimGroup* g) {
+    uint32_t n = 0;
+    if (g)
+        for (const PsimStepper* m : g->ranks) n += m->n;
+    return n;
+}
+
+int psim_group_download_frame(PsimGroup* g, FrameHeader* dst) {
+    if (!g || !dst) return PSIM_EINVAL;
+    g->error.clear();
+    PsimStepper* s = g->ranks[0];
+    uint64_t total = 0;
+    for (PsimStepper* m : g->ranks) {
+        if (!m->has_snapshot) return group_fail(g, fail(s, PSIM_ESTATE, "psim_group_download_frame: no snapshot has been packed"));
+        total += m->snapshot_n;
+    }
+    if (dst->particle_count < total)
+        return group_fail(g, fail(s, PSIM_ECAPACITY, "psim_group_download_frame: destination holds %u particles, "
+                                  "snapshot has %llu", dst->particle_count, (unsigned long long)total));
+    CK(cudaSetDevice(s->device));
+    // slabs in rank order = ascending cell rows = the cell-major order of a single-slab snapshot
+    Particle* out = dst->particles;
+    for (PsimStepper* m : g->ranks) {
+        int rc = download_records(m, out);
+        if (rc) return group_fail(g, rc);
+        out += m->snapshot_n;
+    }
+    write_header(dst, s->snapshot_meta, (uint32_t)total);
     return PSIM_OK;
 }
 

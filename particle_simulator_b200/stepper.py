@@ -41,8 +41,18 @@ class CConfig(ctypes.Structure):
         ("rebin_every", ctypes.c_uint32),
         ("device", ctypes.c_int32),
         ("use_graph", ctypes.c_uint32),
-        ("_reserved", ctypes.c_uint32 * 5),
+        ("slab_rank", ctypes.c_uint32),
+        ("slab_count", ctypes.c_uint32),
+        ("ghost_capacity", ctypes.c_uint32),
+        ("migrant_capacity", ctypes.c_uint32),
+        ("ingest_capacity", ctypes.c_uint32),
     ]
+
+
+class CSlabInfo(ctypes.Structure):
+    _fields_ = [(n, ctypes.c_uint32) for n in (
+        "slab_rank", "slab_count", "first_row", "rows", "first_local_row", "local_rows", "particles",
+        "ghost_below", "ghost_above", "ghost_capacity", "migrant_capacity")] + [("_reserved", ctypes.c_uint32 * 5)]
 
 
 def lib() -> ctypes.CDLL:
@@ -79,9 +89,27 @@ def lib() -> ctypes.CDLL:
             "psim_enable_step_timing": [vp, ctypes.c_int],
             "psim_get_step_timing": [vp, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_uint64)],
             "psim_device_state": [vp, ctypes.POINTER(vp), ctypes.POINTER(vp), ctypes.POINTER(vp), ctypes.POINTER(vp)],
+            "psim_slab_info": [vp, ctypes.POINTER(CSlabInfo)],
+            "psim_comm_unique_id": [vp],
+            "psim_comm_init": [vp, vp],
+            "psim_group_create": [ctypes.POINTER(vp), ctypes.c_uint32, ctypes.POINTER(vp)],
+            "psim_group_upload_frame": [vp, vp],
+            "psim_group_set_metadata": [vp, vp],
+            "psim_group_run_frame_async": [vp],
+            "psim_group_step_async": [vp, ctypes.c_uint32],
+            "psim_group_rebin_async": [vp],
+            "psim_group_snapshot_async": [vp],
+            "psim_group_sync": [vp],
+            "psim_group_download_frame": [vp, vp],
         }.items():
             getattr(L, name).restype = ctypes.c_int
             getattr(L, name).argtypes = args
+        L.psim_group_destroy.restype = None
+        L.psim_group_destroy.argtypes = [vp]
+        L.psim_group_last_error.restype = ctypes.c_char_p
+        L.psim_group_last_error.argtypes = [vp]
+        L.psim_group_particle_count.restype = ctypes.c_uint32
+        L.psim_group_particle_count.argtypes = [vp]
         L.psim_particle_count.restype = ctypes.c_uint32
         L.psim_cell_count.restype = ctypes.c_uint32
         for name in ("psim_steps_executed", "psim_rebins_executed", "psim_kernel_launches"):
@@ -96,7 +124,8 @@ def lib() -> ctypes.CDLL:
 class Stepper:
     def __init__(self, grid_log2: tuple[int, int] = (6, 6), max_particles: int = 65536,
                  schedule: int = SCHEDULE_REFERENCE, rebin_every: int = 0, device: int = -1,
-                 use_graph: bool = False):
+                 use_graph: bool = False, slab_rank: int = 0, slab_count: int = 1, ghost_capacity: int = 0,
+                 migrant_capacity: int = 0, ingest_capacity: int = 0):
         L = lib()
         cfg = L.psim_default_config()
         cfg.grid_x_log2, cfg.grid_y_log2 = grid_log2
@@ -105,6 +134,8 @@ class Stepper:
         cfg.rebin_every = rebin_every
         cfg.device = device
         cfg.use_graph = 1 if use_graph else 0
+        cfg.slab_rank, cfg.slab_count = slab_rank, slab_count
+        cfg.ghost_capacity, cfg.migrant_capacity, cfg.ingest_capacity = ghost_capacity, migrant_capacity, ingest_capacity
         self._h = ctypes.c_void_p()
         rc = L.psim_create(ctypes.byref(cfg), ctypes.byref(self._h))
         if rc != 0:
@@ -178,6 +209,25 @@ class Stepper:
         self._check(lib().psim_download_frame(self._h, frame.ptr))
         return frame
 
+    # -- slab decomposition, one process per slab (NCCL) -------------------------------------
+    @staticmethod
+    def comm_unique_id() -> bytes:
+        """ncclGetUniqueId (rank 0 calls it and distributes the 128 bytes to the other ranks)."""
+        buf = ctypes.create_string_buffer(128)
+        rc = lib().psim_comm_unique_id(buf)
+        if rc != 0:
+            raise PsimError(f"psim_comm_unique_id failed ({rc}): {lib().psim_last_error(None).decode()}")
+        return buf.raw
+
+    def comm_init(self, unique_id: bytes) -> None:
+        assert len(unique_id) == 128
+        self._check(lib().psim_comm_init(self._h, ctypes.c_char_p(unique_id)))
+
+    def slab_info(self) -> dict:
+        info = CSlabInfo()
+        self._check(lib().psim_slab_info(self._h, ctypes.byref(info)))
+        return {n: int(getattr(info, n)) for n, _ in CSlabInfo._fields_ if n != "_reserved"}
+
     # -- introspection -----------------------------------------------------------------------
     @property
     def particle_count(self) -> int:
@@ -211,3 +261,78 @@ class Stepper:
         ms, n = ctypes.c_double(), ctypes.c_uint64()
         self._check(lib().psim_get_step_timing(self._h, ctypes.byref(ms), ctypes.byref(n)))
         return ms.value, n.value
+
+
+class SlabGroup:
+    """All slabs of a row decomposition inside one process on one device (psim_group_*): the same
+    slabs, halo exchange and migration as the one-process-per-GPU NCCL mode, with device-to-device
+    copies as the transport. Results are bit-identical to a single `Stepper` on the same scene."""
+
+    def __init__(self, grid_log2: tuple[int, int], slab_count: int, max_particles_per_slab: int,
+                 ingest_capacity: int = 0, schedule: int = SCHEDULE_REFERENCE, rebin_every: int = 0, device: int = -1,
+                 ghost_capacity: int = 0, migrant_capacity: int = 0):
+        self.slabs = [Stepper(grid_log2, max_particles_per_slab, schedule, rebin_every, device, slab_rank=r,
+                              slab_count=slab_count, ghost_capacity=ghost_capacity,
+                              migrant_capacity=migrant_capacity, ingest_capacity=ingest_capacity if r == 0 else 0)
+                      for r in range(slab_count)]
+        arr = (ctypes.c_void_p * slab_count)(*[s._h for s in self.slabs])
+        self._g = ctypes.c_void_p()
+        rc = lib().psim_group_create(arr, slab_count, ctypes.byref(self._g))
+        if rc != 0:
+            raise PsimError(f"psim_group_create failed ({rc}): {lib().psim_last_error(None).decode()}")
+
+    def _check(self, rc: int) -> None:
+        if rc != 0:
+            raise PsimError(f"psim error {rc}: {lib().psim_group_last_error(self._g).decode()}")
+
+    def close(self) -> None:
+        if getattr(self, "_g", None) and self._g.value:
+            lib().psim_group_destroy(self._g)
+            self._g = ctypes.c_void_p()
+        for s in getattr(self, "slabs", []):
+            s.close()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def upload(self, frame: FrameBuffer) -> None:
+        self._check(lib().psim_group_upload_frame(self._g, frame.ptr))
+
+    def set_metadata(self, metadata: np.ndarray) -> None:
+        meta = np.ascontiguousarray(metadata, dtype=METADATA_DTYPE)
+        self._check(lib().psim_group_set_metadata(self._g, ctypes.c_void_p(meta.ctypes.data)))
+
+    def run_frame_async(self) -> None:
+        self._check(lib().psim_group_run_frame_async(self._g))
+
+    def step_async(self, steps: int = 1) -> None:
+        self._check(lib().psim_group_step_async(self._g, steps))
+
+    def rebin_async(self) -> None:
+        self._check(lib().psim_group_rebin_async(self._g))
+
+    def snapshot_async(self) -> None:
+        self._check(lib().psim_group_snapshot_async(self._g))
+
+    def sync(self) -> None:
+        self._check(lib().psim_group_sync(self._g))
+
+    @property
+    def particle_count(self) -> int:
+        return int(lib().psim_group_particle_count(self._g))
+
+    def download(self, frame: FrameBuffer | None = None) -> FrameBuffer:
+        if frame is None:
+            frame = FrameBuffer(max(self.particle_count, 1))
+        frame.count = frame.capacity
+        self._check(lib().psim_group_download_frame(self._g, frame.ptr))
+        return frame

@@ -1,0 +1,160 @@
+"""Slab decomposition over cell rows on ONE GPU: the in-process slab group
+(psim_group_*, include/psim_b200.h) runs the same slabs, per-step halo exchange and re-bin migration
+as the one-process-per-GPU NCCL mode, with device-to-device copies as the transport.
+
+The reference is single-device, so parity here is with our own single-slab run, and it is BIT-EXACT:
+every particle accumulates its stencil neighbours in the same order whatever slab it lives in, and
+migrants are merged in the order they have in the global cell-sorted array.
+"""
+import numpy as np
+import pytest
+
+from conftest import frame_from
+from particle_simulator_b200 import FrameBuffer, io
+
+pytestmark = pytest.mark.gpu
+
+
+def run_both(fb: FrameBuffer, grid, slabs: int, frames: int, per_slab_capacity: int | None = None):
+    """Run `frames` frames single-slab and as a slab group; yield (single, group, the group) per frame."""
+    from particle_simulator_b200.stepper import SlabGroup, Stepper
+
+    n = fb.count
+    cap = per_slab_capacity or n
+    with Stepper(grid, n) as st, SlabGroup(grid, slabs, cap, ingest_capacity=n) as gr:
+        st.upload(fb)
+        gr.upload(fb)
+        assert gr.particle_count == st.particle_count
+        assert st.download().particles.tobytes() == gr.download().particles.tobytes()  # the ingested scene
+        for _ in range(frames):
+            st.run_frame_async()
+            gr.run_frame_async()
+            st.sync()
+            gr.sync()
+            yield st.download().particles.copy(), gr.download().particles.copy(), gr
+        assert [s.steps_executed for s in gr.slabs] == [st.steps_executed] * slabs
+        assert [s.rebins_executed for s in gr.slabs] == [st.rebins_executed] * slabs
+
+
+@pytest.mark.parametrize("slabs", [2, 4, 8])
+@pytest.mark.parametrize("scene", ["hex2500", "gas10k", "wall_cursor"])
+def test_group_is_bit_identical_to_single_slab(golden, scene, slabs):
+    g = golden(scene)
+    meta = g["meta"][0].copy()
+    meta["steps_per_frame"] = 35  # 36 steps, 2 re-bins per frame on the reference schedule
+    fb = frame_from(g["input"], meta)
+    stages = 0
+    for single, group, _ in run_both(fb, (6, 6), slabs, frames=3):
+        assert len(single) == len(group) == fb.count
+        assert single.tobytes() == group.tobytes()
+        stages += 1
+    assert stages == 3
+
+
+def test_ingest_and_fine_grained_calls_match(golden):
+    from particle_simulator_b200.stepper import SlabGroup, Stepper
+
+    g = golden("liquid4k")
+    fb = frame_from(g["input"], g["meta"][0])
+    with Stepper((6, 6), fb.count) as st, SlabGroup((6, 6), 4, fb.count, ingest_capacity=fb.count) as gr:
+        st.upload(fb)
+        gr.upload(fb)
+        # the ingested scene: golden binning of the reference (kernel.cuh:210-239), slab by slab
+        assert gr.download().particles.tobytes() == g["binned"].tobytes()
+        rows = [s.slab_info() for s in gr.slabs]
+        assert [r["first_row"] for r in rows] == [0, 16, 32, 48] and all(r["rows"] == 16 for r in rows)
+        assert [r["local_rows"] for r in rows] == [17, 18, 18, 17]
+        assert sum(r["particles"] for r in rows) == fb.count
+        # a slab's ghost rows are its neighbours' boundary rows
+        cs = [s.cell_start() for s in gr.slabs]
+        for r in range(3):
+            top_row_of_r = np.diff(cs[r])[-2 * 64:-64]
+            ghost_below_next = np.diff(cs[r + 1])[:64]
+            assert np.array_equal(top_row_of_r, ghost_below_next)
+        for k in range(1, 40):
+            st.step_async(1)
+            gr.step_async(1)
+            if k % 9 == 0:
+                st.rebin_async()
+                gr.rebin_async()
+            st.snapshot_async()
+            gr.snapshot_async()
+            assert st.download().particles.tobytes() == gr.download().particles.tobytes(), f"step {k}"
+
+
+def test_particles_migrate_between_slabs(golden):
+    """The hot gas crosses slab boundaries: ownership moves, nothing is lost or duplicated."""
+    g = golden("gas10k")
+    meta = g["meta"][0].copy()
+    meta["steps_per_frame"] = 100
+    fb = frame_from(g["input"], meta)
+    counts = []
+    for single, group, gr in run_both(fb, (6, 6), 4, frames=4):
+        assert single.tobytes() == group.tobytes()
+        counts.append([s.particle_count for s in gr.slabs])
+        assert sum(counts[-1]) == fb.count
+    assert len({tuple(c) for c in counts}) > 1, counts  # ownership really changed
+
+
+def test_liquid_1m_in_8_slabs():
+    """configs[1]-sized: 1M particles melting at 150-250 m/s, 1024x1024 cells, 8 slabs of 128 rows."""
+    from particle_simulator_b200.workloads import config_1m_liquid
+
+    w = config_1m_liquid()
+    w.frame.metadata["steps_per_frame"] = 52  # 52 steps, 3 re-bins
+    n = 0
+    for single, group, gr in run_both(w.frame, w.grid_log2, 8, frames=2, per_slab_capacity=w.particles // 4):
+        assert single.tobytes() == group.tobytes()
+        n += 1
+    assert n == 2
+
+
+def test_native_schedule_matches_too(golden):
+    from particle_simulator_b200.stepper import SCHEDULE_NATIVE, SlabGroup, Stepper
+
+    g = golden("gas10k")
+    meta = g["meta"][0].copy()
+    meta["steps_per_frame"] = 25
+    fb = frame_from(g["input"], meta)
+    with Stepper((6, 6), fb.count, schedule=SCHEDULE_NATIVE, rebin_every=7) as st, \
+            SlabGroup((6, 6), 2, fb.count, ingest_capacity=fb.count, schedule=SCHEDULE_NATIVE, rebin_every=7) as gr:
+        st.upload(fb)
+        gr.upload(fb)
+        for _ in range(3):
+            st.run_frame_async()
+            gr.run_frame_async()
+            st.sync()
+            gr.sync()
+            assert st.download().particles.tobytes() == gr.download().particles.tobytes()
+        assert st.steps_executed == 75 and gr.slabs[0].steps_executed == 75
+        assert st.rebins_executed == gr.slabs[1].rebins_executed == 10
+
+
+def test_particle_that_skips_a_slab_is_reported_not_lost():
+    from particle_simulator_b200.stepper import PsimError, SlabGroup
+
+    fb = FrameBuffer(2501)
+    io.scene_hex_square(fb, 50, 50, (25e-9, 25e-9), 1.0, 5.0, 5.0, 0, seed=7)
+    p = fb.particles[:1].copy()
+    p["x"], p["y"], p["vx"], p["vy"] = 1 << 28, 1 << 28, 0.0, 40000.0  # 34 nm in 17 steps = 43 cell rows
+    fb.set_particles(np.concatenate([fb.particles, p]))
+    fb.metadata["steps_per_frame"] = 36  # the second re-bin comes 17 steps after the first
+    with SlabGroup((6, 6), 8, 2501, ingest_capacity=2501) as gr:
+        gr.upload(fb)
+        with pytest.raises(PsimError, match="moved past the adjacent slab"):
+            gr.run_frame_async()
+            gr.sync()
+
+
+def test_bad_slab_configurations_are_rejected():
+    from particle_simulator_b200.stepper import PsimError, Stepper
+
+    with pytest.raises(PsimError, match="do not split"):
+        Stepper((6, 6), 100, slab_rank=0, slab_count=3)
+    with pytest.raises(PsimError, match="slab_rank"):
+        Stepper((6, 6), 100, slab_rank=2, slab_count=2)
+    with Stepper((6, 6), 100, slab_rank=1, slab_count=2) as st:
+        fb = FrameBuffer(4)
+        io.scene_hex_square(fb, 2, 2, (25e-9, 40e-9), 1.0, 5.0, 5.0, 0, seed=7)
+        with pytest.raises(PsimError, match="psim_comm_init"):
+            st.upload(fb)  # a lone slab of two must have joined its communicator first
