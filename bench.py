@@ -188,35 +188,52 @@ def run_ours(args, rank: int, world: int, local_rank: int) -> None:
     import torch
     import torch.distributed as dist
 
-    from particle_simulator_b200 import workloads
+    from particle_simulator_b200 import slabs, workloads
     from particle_simulator_b200.frame import FrameBuffer, packet_size
     from particle_simulator_b200.stepper import Stepper
 
     torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
     if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        dist.init_process_group("nccl", device_id=dev)
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
+    def over_ranks(x: float, op: str) -> float:
+        return slabs.reduce_scalar(dist, x, op, device=dev) if world > 1 else x
+
     # the scene lives in page-locked host memory: it is what the e2e leg uploads every step
-    n_cap = 3162 * 3163
-    keep_in, store_in = pinned_storage(packet_size(n_cap))
-    keep_out, store_out = pinned_storage(packet_size(n_cap))
-    wl = workloads.config_10m_solid(storage=store_in)
-    wl.frame.metadata["steps_per_frame"] = STEPS_PER_FRAME
-    n = wl.particles
-    out = FrameBuffer(n, storage=store_out)
-    executed = schedule_steps(STEPS_PER_FRAME)
+    keep = []
+
+    def pinned_frame_storage(count: int) -> np.ndarray:
+        t, a = pinned_storage(packet_size(count))
+        keep.append(t)
+        return a
 
     stream = torch.cuda.Stream()
-    st = Stepper(wl.grid_log2, n, device=local_rank)
+    if world == 1:
+        wl = workloads.config_10m_solid(storage=pinned_frame_storage(3162 * 3163))
+        st = Stepper(wl.grid_log2, wl.particles, device=local_rank)
+    else:
+        # weak scaling: one crystal across `world` slabs of 2048 cell rows, ~10M particles per slab; rank r
+        # steps slab r, halo rows and migrants travel over NCCL send/recv (NVLink)
+        wl = workloads.slab_crystal(rank, world, storage_factory=pinned_frame_storage)
+        uid = slabs.broadcast_bytes(dist, Stepper.comm_unique_id() if rank == 0 else None, 128, device=dev)
+        st = Stepper(wl.grid_log2, int(1.05 * 3162 * 3163), device=local_rank, slab_rank=rank, slab_count=world,
+                     ingest_capacity=wl.frame.count)
+        st.comm_init(uid)
+    wl.frame.metadata["steps_per_frame"] = STEPS_PER_FRAME
+    executed = schedule_steps(STEPS_PER_FRAME)
     st.set_stream(stream.cuda_stream)
 
     # ---- device-resident leg -------------------------------------------------------------------
     st.upload(wl.frame)
+    n_local = st.particle_count
+    n = int(over_ranks(float(n_local), "sum"))  # particles of the whole job
+    out = FrameBuffer(n_local, storage=pinned_frame_storage(n_local))
     for _ in range(args.warmup):
         st.run_frame_async()
     st.sync()
@@ -241,11 +258,8 @@ def run_ours(args, rank: int, world: int, local_rank: int) -> None:
     launches = st.kernel_launches - launches0
     steps_done = st.steps_executed - steps0
     assert steps_done == executed * args.steps
-    if world > 1:
-        t = torch.tensor([ms], device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms = float(t.item())
-    value = world * n * steps_done / (ms * 1e-3)
+    ms = over_ranks(ms, "max")
+    value = n * steps_done / (ms * 1e-3)
 
     # ---- end-to-end leg: host frame in, host frame out, every step -------------------------------
     for _ in range(min(args.warmup, 2)):
@@ -260,34 +274,39 @@ def run_ours(args, rank: int, world: int, local_rank: int) -> None:
         st.download(out)
     torch.cuda.synchronize()
     t_e2e = time.perf_counter() - t0
-    if world > 1:
-        t = torch.tensor([t_e2e], device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        t_e2e = float(t.item())
-    assert out.count == n
-    e2e_value = world * n * executed * args.steps / t_e2e
+    t_e2e = over_ranks(t_e2e, "max")
+    assert out.count == n_local
+    e2e_value = n * executed * args.steps / t_e2e
+    h2d = int(over_ranks(float(packet_size(wl.frame.count)), "sum"))
+    d2h = int(over_ranks(float(packet_size(n_local)), "sum"))
+    kernel_ms_max = over_ranks(step_ms / max(step_launches, 1), "max")
+    launches = int(over_ranks(float(launches), "sum"))
 
     if rank == 0:
         peak, peak_src = measured_hbm_peak()
         kernel_ms = step_ms / max(step_launches, 1)
-        achieved = ALGO_BYTES_PER_UPDATE * n / (kernel_ms * 1e-3) / 1e9
+        achieved = ALGO_BYTES_PER_UPDATE * n_local / (kernel_ms * 1e-3) / 1e9  # per GPU (rank 0's slab)
         line = {
             "metric": "particle-updates/sec at 10M particles", "value": value, "unit": "particle-updates/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": wl.name, "description": wl.description, "particles": n,
+                       "particles_rank0": n_local,
                        "steps_per_frame": STEPS_PER_FRAME, "leapfrog_steps_per_bench_step": executed,
                        "rebins_per_bench_step": 6, "schedule": "reference (kernel_bucket.cuh:181-206)",
-                       "l2": "state (10M x 20 B x 2 buffers = 400 MB) is larger than the 126 MB L2; no flush",
-                       "replicas": world},
+                       "l2": "state (10M x 20 B x 2 buffers = 400 MB per GPU) is larger than the 126 MB L2; "
+                             "no flush",
+                       "decomposition": "single slab" if world == 1 else
+                       f"{world} slabs of 2048 cell rows, one per GPU; per step: NCCL send/recv of the two "
+                       "boundary rows' positions; per re-bin: migrants + boundary-row cell counts"},
             "roofline": {"bound": "hbm", "kernel": "step_kernel (fused 3x3-cell force + kick + drift)",
                          "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "peak_source": peak_src, "traffic": recorded_traffic(),
-                         "algorithmic_bytes_per_launch": ALGO_BYTES_PER_UPDATE * n,
-                         "kernel_ms": kernel_ms, "kernel_launches_timed": step_launches,
+                         "algorithmic_bytes_per_launch": ALGO_BYTES_PER_UPDATE * n_local,
+                         "kernel_ms": kernel_ms, "kernel_ms_max_over_ranks": kernel_ms_max, "kernel_launches_timed": step_launches,
                          "kernel_share_of_step": step_ms / ms},
-            "e2e": {"value": e2e_value, "unit": "particle-updates/s", "h2d_bytes_per_step": packet_size(n),
-                    "d2h_bytes_per_step": packet_size(n), "ms_per_step": 1e3 * t_e2e / args.steps},
+            "e2e": {"value": e2e_value, "unit": "particle-updates/s", "h2d_bytes_per_step": h2d,
+                    "d2h_bytes_per_step": d2h, "ms_per_step": 1e3 * t_e2e / args.steps},
             "gpu_launches": launches,
             "clocks": clocks,
         }

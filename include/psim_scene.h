@@ -26,6 +26,12 @@ int psim_scene_hex_square(FrameHeader* frame, uint32_t capacity, uint32_t nx, ui
 int psim_scene_square(FrameHeader* frame, uint32_t capacity, uint32_t nx, uint32_t ny, double center_x,
                       double center_y, float distance_factor, float v_min, float v_max, int32_t ty,
                       uint64_t seed);
+/* Lattice rows [row_begin, row_end) of the nx * ny hex lattice centred on (center_x, center_y): the same
+ * geometry as psim_scene_hex_square, emitted row by row with one velocity stream per lattice row, so that
+ * every slab of a row decomposition can generate its own part of one global crystal independently. */
+int psim_scene_hex_rows(FrameHeader* frame, uint32_t capacity, uint32_t nx, uint32_t ny, uint32_t row_begin,
+                        uint32_t row_end, double center_x, double center_y, float distance_factor, float v_min,
+                        float v_max, int32_t ty, uint64_t seed);
 /* Gas: `count` particles at uniformly random positions at least `margin` metres from the walls and
  * at least `min_dist` metres from each other and from the particles already in the frame
  * (rejection sampling), speeds as above. */

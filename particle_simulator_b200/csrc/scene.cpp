@@ -84,6 +84,33 @@ int psim_scene_hex_square(FrameHeader* frame, uint32_t capacity, uint32_t nx, ui
     return 0;
 }
 
+int psim_scene_hex_rows(FrameHeader* frame, uint32_t capacity, uint32_t nx, uint32_t ny, uint32_t row_begin,
+                        uint32_t row_end, double center_x, double center_y, float distance_factor, float v_min,
+                        float v_max, int32_t ty, uint64_t seed) {
+    if (row_end > ny || row_begin > row_end) return -1;
+    uint64_t total = (uint64_t)nx * (row_end - row_begin);
+    if (total == 0) return 0;
+    if ((uint64_t)frame->particle_count + total > capacity) return -1;
+    const FrameMetadata meta = frame->metadata;
+    int species = ty > 0 && ty < 2 ? ty : 0;
+    double rx = psim_force0_r(meta.particles[species]) * (double)distance_factor;
+    double ry = std::sin(3.14159265358979323846 / 3.) * rx;
+    double start_x = center_x - rx * (double)(nx - 1) / 2.;
+    double start_y = center_y - ry * (double)(ny - 1) / 2.;
+    Particle* out = frame->particles + frame->particle_count;
+    for (uint32_t iy = row_begin; iy < row_end; ++iy) {
+        Rng rng(seed ^ (0xD1B54A32D192ED03ull * (uint64_t)(iy + 1)));  // one stream per lattice row
+        double offset = iy % 2 == 0 ? 0. : rx / 2.;
+        for (uint32_t ix = 0; ix < nx; ++ix) {
+            double vx, vy;
+            random_vel(rng, v_min, v_max, &vx, &vy);
+            *out++ = new_particle(meta, start_x + rx * (double)ix + offset, start_y + ry * (double)iy, vx, vy, ty);
+        }
+    }
+    frame->particle_count += (uint32_t)total;
+    return 0;
+}
+
 int psim_scene_square(FrameHeader* frame, uint32_t capacity, uint32_t nx, uint32_t ny, double center_x,
                       double center_y, float distance_factor, float v_min, float v_max, int32_t ty,
                       uint64_t seed) {  // presets.rs:48-74

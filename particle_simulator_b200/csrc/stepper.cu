@@ -721,7 +721,15 @@ __global__ void migrant_pack_kernel(const uint2* __restrict__ pos, const float2*
         header->count = count;
         header->_pad[0] = header->_pad[1] = header->_pad[2] = 0;
     }
-    if (e >= count) return;
+    if (e >= box_capacity) return;
+    if (e >= count) {  // the rest of the box is null records (ty < 0): the receiver scans the whole box
+        Particle q;
+        q.x = q.y = 0;
+        q.vx = q.vy = 0.f;
+        q.ty = -1;
+        rec[e] = q;
+        return;
+    }
     uint32_t i = idx[e];
     uint32_t r = 0;
     for (uint32_t k = 0; k < count; ++k) r += idx[k] < i ? 1u : 0u;

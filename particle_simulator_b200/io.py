@@ -80,6 +80,10 @@ def lib() -> ctypes.CDLL:
         L.psim_scene_hex_square.argtypes = lattice
         L.psim_scene_square.restype = ctypes.c_int
         L.psim_scene_square.argtypes = lattice
+        L.psim_scene_hex_rows.restype = ctypes.c_int
+        L.psim_scene_hex_rows.argtypes = [vp, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_uint32,
+                                          ctypes.c_uint32, ctypes.c_double, ctypes.c_double, ctypes.c_float,
+                                          ctypes.c_float, ctypes.c_float, ctypes.c_int32, ctypes.c_uint64]
         L.psim_scene_gas.restype = ctypes.c_int
         L.psim_scene_gas.argtypes = [vp, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_double, ctypes.c_double,
                                      ctypes.c_float, ctypes.c_float, ctypes.c_int32, ctypes.c_uint64]
@@ -192,6 +196,16 @@ def scene_hex_square(frame: FrameBuffer, nx: int, ny: int, center: tuple[float, 
                                      v_min, v_max, ty, seed)
     if rc != 0:
         raise ValueError("hex_square: frame too small or bad arguments")
+
+
+def scene_hex_rows(frame: FrameBuffer, nx: int, ny: int, rows: tuple[int, int], center: tuple[float, float],
+                   distance_factor: float = 1.0, v_min: float = 0.0, v_max: float = 0.0, ty: int = 0,
+                   seed: int = 0) -> None:
+    """Lattice rows [rows[0], rows[1]) of the nx x ny hex lattice centred on `center` (psim_scene_hex_rows)."""
+    rc = lib().psim_scene_hex_rows(frame.ptr, frame.capacity, nx, ny, rows[0], rows[1], center[0], center[1],
+                                   distance_factor, v_min, v_max, ty, seed)
+    if rc != 0:
+        raise ValueError("hex_rows: frame too small or bad arguments")
 
 
 def scene_square(frame: FrameBuffer, nx: int, ny: int, center: tuple[float, float], distance_factor: float = 1.0,

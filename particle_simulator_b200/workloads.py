@@ -11,7 +11,7 @@ from dataclasses import dataclass
 import numpy as np
 
 from . import io
-from .frame import FrameBuffer
+from .frame import FrameBuffer, default_metadata
 
 CELL_WIDTH = 50e-9 / 64
 
@@ -61,7 +61,42 @@ def config_1m_liquid(storage: np.ndarray | None = None) -> Workload:
     return lattice(1000, 1000, (10, 10), 1.05, 150.0, 250.0, seed=1, storage=storage, name="1M-liquid")
 
 
-def slab_lattice(rank: int, nranks: int, rows_per_rank_log2: int = 11, storage: np.ndarray | None = None) -> Workload:
-    """Weak-scaling workload: every rank owns a 2048-row slab holding its own 10M-particle lattice; the global
-    grid is 2048 x (2048 * nranks) cells."""
-    raise NotImplementedError
+def slab_crystal_geometry(world: int, per_slab: int = 3162 * 3163, rows_per_slab_log2: int = 11,
+                          grid_x_log2: int = 11, margin_cells: int = 4) -> dict:
+    """Weak-scaling workload (BASELINE.json: 1/2/4/8 B200): ONE hex crystal at r0 spanning `world` slabs of
+    2048 cell rows each, `per_slab` particles per slab on average, so that every slab holds the same work and
+    every slab boundary cuts through the crystal (real halo traffic, real migration). The box grows in y only:
+    2048 x (2048 * world) cells of the reference's cell width."""
+    assert world >= 1 and world & (world - 1) == 0, "slab counts are powers of two (the grid is)"
+    meta = default_metadata()
+    grid = (grid_x_log2, rows_per_slab_log2 + world.bit_length() - 1)
+    width, height = CELL_WIDTH * (1 << grid[0]), CELL_WIDTH * (1 << grid[1])
+    meta["box_width"], meta["box_height"] = width, height
+    r0 = io.force0_r(meta)
+    ry = float(np.sin(np.pi / 3)) * r0
+    ny = int((height - 2 * margin_cells * CELL_WIDTH) / ry)
+    nx = int(round(per_slab * world / ny))
+    assert nx * r0 < width - 2 * margin_cells * CELL_WIDTH
+    return {"grid_log2": grid, "box": (width, height), "nx": nx, "ny": ny, "r0": r0, "ry": ry,
+            "start_y": height / 2 - ry * (ny - 1) / 2}
+
+
+def slab_crystal(rank: int, world: int, storage_factory=None, per_slab: int = 3162 * 3163,
+                 rows_per_slab_log2: int = 11, grid_x_log2: int = 11, seed: int = 3) -> Workload:
+    """The lattice rows of slab_crystal_geometry() that fall into slab `rank` (plus one row either side: the
+    stepper keeps the records of its own cell rows and skips the rest, kernel.cuh:222-226 semantics)."""
+    geo = slab_crystal_geometry(world, per_slab, rows_per_slab_log2, grid_x_log2)
+    width, height = geo["box"]
+    slab_h = height / world
+    lo = int(np.floor((rank * slab_h - geo["start_y"]) / geo["ry"])) - 1
+    hi = int(np.ceil(((rank + 1) * slab_h - geo["start_y"]) / geo["ry"])) + 1
+    lo, hi = max(lo, 0), min(hi, geo["ny"])
+    count = geo["nx"] * (hi - lo)
+    storage = storage_factory(count) if storage_factory else None
+    fb = FrameBuffer(count, storage=storage)
+    fb.metadata["box_width"], fb.metadata["box_height"] = width, height
+    io.scene_hex_rows(fb, geo["nx"], geo["ny"], (lo, hi), (width / 2, height / 2), 1.0, 1.0, 10.0, 0, seed)
+    desc = (f"one {geo['nx']}x{geo['ny']} hex crystal at 1 r0 across {world} slabs of {1 << rows_per_slab_log2} "
+            f"cell rows, speeds 1-10 m/s, {1 << geo['grid_log2'][0]}x{1 << geo['grid_log2'][1]} cells, box "
+            f"{width * 1e6:.2f}x{height * 1e6:.2f} um; slab {rank} is handed lattice rows [{lo}, {hi})")
+    return Workload(f"10M-solid-lattice-per-slab-x{world}", desc, geo["grid_log2"], fb)

@@ -1,0 +1,69 @@
+"""One rank of the NCCL slab test (launched by torchrun from tests/test_gpu_nccl.py, one process per GPU).
+
+Every rank owns one slab of the 1M-particle melting liquid (BASELINE.json configs[1]); halo exchange and
+migration go through NCCL send/recv (psim_comm_init). After every frame the slabs' snapshots, concatenated
+in rank order, must be byte-identical to the single-slab run of the same scene (rank 0 runs it too)."""
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, REPO)
+
+from particle_simulator_b200 import slabs, workloads  # noqa: E402
+from particle_simulator_b200.stepper import Stepper  # noqa: E402
+
+
+def main() -> int:
+    rank, world, local = (int(os.environ[k]) for k in ("RANK", "WORLD_SIZE", "LOCAL_RANK"))
+    torch.cuda.set_device(local)
+    dist.init_process_group("gloo")
+    frames = int(sys.argv[1]) if len(sys.argv) > 1 else 3
+    wl = workloads.config_1m_liquid()
+    wl.frame.metadata["steps_per_frame"] = 52  # 52 steps, 3 re-bins
+    n = wl.particles
+    uid = slabs.broadcast_bytes(dist, Stepper.comm_unique_id() if rank == 0 else None, 128)
+    st = Stepper(wl.grid_log2, n // 2 if world > 1 else n, device=local, slab_rank=rank, slab_count=world,
+                 ingest_capacity=n)
+    st.comm_init(uid)
+    single = Stepper(wl.grid_log2, n, device=local) if rank == 0 else None
+    st.upload(wl.frame)  # the whole scene: the slab keeps its own rows
+    if single:
+        single.upload(wl.frame)
+    ok = True
+    counts_seen = set()
+    for frame in range(frames + 1):
+        if frame:
+            st.run_frame_async()
+            st.sync()
+            if single:
+                single.run_frame_async()
+                single.sync()
+        mine = st.download().particles.tobytes()
+        gathered = [None] * world if rank == 0 else None
+        dist.gather_object(mine, gathered, 0)
+        if rank == 0:
+            want = single.download().particles.tobytes()
+            got = b"".join(gathered)
+            same = got == want
+            counts = tuple(len(g) // 20 for g in gathered)
+            counts_seen.add(counts)
+            print(f"frame {frame}: slabs hold {counts}, identical to the single-slab run: {same}", flush=True)
+            ok = ok and same and sum(counts) == n
+    if rank == 0 and world > 1 and len(counts_seen) < 2:
+        print("no particle ever changed slab: the migration path was not exercised", flush=True)
+        ok = False
+    flag = torch.tensor([1 if ok else 0])
+    dist.broadcast(flag, 0)
+    st.close()
+    if single:
+        single.close()
+    dist.destroy_process_group()
+    return 0 if int(flag.item()) else 1
+
+
+if __name__ == "__main__":
+    sys.exit(main())

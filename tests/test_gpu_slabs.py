@@ -103,7 +103,7 @@ def test_liquid_1m_in_8_slabs():
     w = config_1m_liquid()
     w.frame.metadata["steps_per_frame"] = 52  # 52 steps, 3 re-bins
     n = 0
-    for single, group, gr in run_both(w.frame, w.grid_log2, 8, frames=2, per_slab_capacity=w.particles // 4):
+    for single, group, gr in run_both(w.frame, w.grid_log2, 8, frames=2, per_slab_capacity=w.particles // 2):
         assert single.tobytes() == group.tobytes()
         n += 1
     assert n == 2
