@@ -763,6 +763,7 @@ struct NcclApi {
     int (*GetUniqueId)(ncclUniqueId*) = nullptr;
     int (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
     int (*CommDestroy)(ncclComm_t) = nullptr;
+    int (*CommAbort)(ncclComm_t) = nullptr;
     int (*Send)(const void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
     int (*Recv)(void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
     int (*GroupStart)() = nullptr;
@@ -852,6 +853,7 @@ struct PsimStepper {
     uint64_t timing_launches = 0;
 
     std::string error;
+    bool failed = false;  // a call failed while a communicator exists: peers may be waiting for this slab
 };
 
 struct PsimGroup {
@@ -872,8 +874,12 @@ int fail(PsimStepper* s, int code, const char* fmt, ...) {
     va_start(ap, fmt);
     vsnprintf(buf, sizeof buf, fmt, ap);
     va_end(ap);
-    if (s) s->error = buf;
-    else g_create_error = buf;
+    if (s) {
+        s->error = buf;
+        s->failed = true;
+    } else {
+        g_create_error = buf;
+    }
     return code;
 }
 
@@ -1088,6 +1094,7 @@ bool load_nccl(PsimStepper* s) {
     api.GetUniqueId = reinterpret_cast<decltype(api.GetUniqueId)>(sym("ncclGetUniqueId"));
     api.CommInitRank = reinterpret_cast<decltype(api.CommInitRank)>(sym("ncclCommInitRank"));
     api.CommDestroy = reinterpret_cast<decltype(api.CommDestroy)>(sym("ncclCommDestroy"));
+    api.CommAbort = reinterpret_cast<decltype(api.CommAbort)>(sym("ncclCommAbort"));
     api.Send = reinterpret_cast<decltype(api.Send)>(sym("ncclSend"));
     api.Recv = reinterpret_cast<decltype(api.Recv)>(sym("ncclRecv"));
     api.GroupStart = reinterpret_cast<decltype(api.GroupStart)>(sym("ncclGroupStart"));
@@ -1580,6 +1587,11 @@ const char* psim_last_error(const PsimStepper* s) { return s ? s->error.c_str() 
 void psim_destroy(PsimStepper* s) {
     if (!s) return;
     cudaSetDevice(s->device);
+    // after a failure the exchanges still queued on the stream would wait for peers for ever: abort them
+    if (s->comm && s->failed && g_nccl.CommAbort) {
+        g_nccl.CommAbort(s->comm);
+        s->comm = nullptr;
+    }
     if (s->stream) cudaStreamSynchronize(s->stream);
     if (s->copy_stream) cudaStreamSynchronize(s->copy_stream);
     if (s->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(s->comm);

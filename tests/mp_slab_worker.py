@@ -26,7 +26,8 @@ def main() -> int:
     wl.frame.metadata["steps_per_frame"] = 52  # 52 steps, 3 re-bins
     n = wl.particles
     uid = slabs.broadcast_bytes(dist, Stepper.comm_unique_id() if rank == 0 else None, 128)
-    st = Stepper(wl.grid_log2, n // 2 if world > 1 else n, device=local, slab_rank=rank, slab_count=world,
+    # the lattice splits evenly at first and melts across the boundaries: leave room for the imbalance
+    st = Stepper(wl.grid_log2, int(0.75 * n) if world > 1 else n, device=local, slab_rank=rank, slab_count=world,
                  ingest_capacity=n)
     st.comm_init(uid)
     single = Stepper(wl.grid_log2, n, device=local) if rank == 0 else None
@@ -66,4 +67,13 @@ def main() -> int:
 
 
 if __name__ == "__main__":
-    sys.exit(main())
+    try:
+        code = main()
+    except BaseException:  # a rank that dies must not leave its peers waiting in a collective
+        import traceback
+
+        traceback.print_exc()
+        sys.stderr.flush()
+        os._exit(1)
+    sys.stdout.flush()
+    os._exit(code)

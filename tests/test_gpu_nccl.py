@@ -1,6 +1,7 @@
 """Slab decomposition with one process per GPU and NCCL as the transport (needs >= 2 GPUs; on a one-GPU
 box the same slabs are covered by tests/test_gpu_slabs.py through the in-process group)."""
 import os
+import signal
 import subprocess
 import sys
 
@@ -23,7 +24,15 @@ def test_nccl_slabs_are_bit_identical_to_single_slab(world):
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}",
            "--master-addr", "127.0.0.1", "--master-port", str(29600 + world),
            os.path.join(REPO, "tests", "mp_slab_worker.py"), "3"]
-    proc = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=REPO)
-    sys.stdout.write(proc.stdout[-4000:])
-    assert proc.returncode == 0, proc.stdout[-4000:] + proc.stderr[-4000:]
-    assert "identical to the single-slab run: True" in proc.stdout
+    # own session: if a rank hangs, the whole process group is killed, never left spinning on the GPUs
+    proc = subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, cwd=REPO,
+                            start_new_session=True)
+    try:
+        out, err = proc.communicate(timeout=240)
+    except subprocess.TimeoutExpired:
+        os.killpg(proc.pid, signal.SIGKILL)
+        out, err = proc.communicate()
+        pytest.fail("NCCL slab worker timed out\n" + out[-3000:] + err[-3000:])
+    sys.stdout.write(out[-4000:])
+    assert proc.returncode == 0, out[-4000:] + err[-4000:]
+    assert "identical to the single-slab run: True" in out and "run: False" not in out
