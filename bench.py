@@ -240,14 +240,16 @@ def run_ours(args, rank: int, world: int, local_rank: int) -> None:
     barrier()
     sampler = ClockSampler(local_rank)
     sampler.start()
-    st.enable_step_timing(True)
+    st.enable_step_timing(not args.no_step_timing)
     launches0 = st.kernel_launches
     steps0 = st.steps_executed
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     e0.record(stream)
+    t_host = time.perf_counter()
     for _ in range(args.steps):
         st.run_frame_async()
+    t_host = time.perf_counter() - t_host  # host time to enqueue the timed frames (launch-bound if ~ms)
     e1.record(stream)
     st.sync()
     barrier()
@@ -308,6 +310,7 @@ def run_ours(args, rank: int, world: int, local_rank: int) -> None:
             "e2e": {"value": e2e_value, "unit": "particle-updates/s", "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h, "ms_per_step": 1e3 * t_e2e / args.steps},
             "gpu_launches": launches,
+            "host_enqueue_ms_per_step": 1e3 * t_host / args.steps,
             "clocks": clocks,
         }
         if world == 1 and not args.no_cpu_baseline:
@@ -327,6 +330,7 @@ def main() -> None:
     ap.add_argument("--ref-steps", type=int, default=2, help="--impl reference: steps_per_frame of one bench step")
     ap.add_argument("--cpu-steps", type=int, default=3, help="cpu_baseline: steps_per_frame of the sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-step-timing", action="store_true", help="no CUDA events around the step-kernel launches")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

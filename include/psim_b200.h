@@ -120,6 +120,19 @@ int psim_get_cell_start(PsimStepper* s, uint32_t* out);
 int psim_enable_step_timing(PsimStepper* s, int enable);
 int psim_get_step_timing(PsimStepper* s, double* total_ms, uint64_t* launches);
 
+/* How the step kernel's tiles look after the last binning: which kernel runs (float_path = 1: step_kernel_c,
+ * two cell-mates per thread on exact fp32 offsets, grids of >= 1024 cells per axis; 0: step_kernel, one particle
+ * per thread on integer separations) and how many tiles stage their stencil in shared memory (the others read
+ * global memory: very sparse or very crowded spots). Synchronises. */
+typedef struct PsimTileStats {
+    uint32_t float_path;
+    uint32_t tiles, tiles_staged;
+    uint32_t max_columns, max_row_particles;
+    uint32_t _reserved;
+    uint64_t threads_live, threads_launched;
+} PsimTileStats;
+int psim_tile_stats(PsimStepper* s, PsimTileStats* out);
+
 /* Where this stepper's slab sits and what it currently holds. */
 typedef struct PsimSlabInfo {
     uint32_t slab_rank, slab_count;

@@ -336,6 +336,19 @@ struct StepArgs {
     Phys ph;
 };
 
+// Cursor + wall force, pair sum, kick + drift and the two stores of one particle (shared by all step kernels).
+__device__ __forceinline__ void finish_particle(uint32_t i, uint2 pi, float2 vi, float sum_x, float sum_y,
+                                                float scale_x, float scale_y, const StepArgs& a) {
+    float2 f = field_force(pi, a.ph);
+    f.x = fmaf(scale_x, sum_x, f.x);
+    f.y = fmaf(scale_y, sum_y, f.y);
+    uint2 po;
+    float2 vo;
+    integrate(pi, vi, f, a.ph, po, vo);
+    a.pos_out[i] = po;
+    a.vel[i] = vo;
+}
+
 template <int KN, int FRAC, bool ANISO>
 __device__ __forceinline__ void step_particle(uint32_t i, uint2 pi, float2 vi, uint32_t cell,
                                               const uint32_t* const cs[3], const uint32_t cs_lo[3],
@@ -354,14 +367,7 @@ __device__ __forceinline__ void step_particle(uint32_t i, uint2 pi, float2 vi, u
         if (d == 1) window_accumulate<KN, FRAC, ANISO, true>(win, (int)(e - s), pi, a.ph, gx, gy);  // contains i
         else window_accumulate<KN, FRAC, ANISO, false>(win, (int)(e - s), pi, a.ph, gx, gy);
     }
-    float2 f = field_force(pi, a.ph);
-    f.x = fmaf(a.ph.pair_scale, gx.x + gx.y, f.x);
-    f.y = fmaf(a.ph.pair_scale_y, gy.x + gy.y, f.y);
-    uint2 po;
-    float2 vo;
-    integrate(pi, vi, f, a.ph, po, vo);
-    a.pos_out[i] = po;
-    a.vel[i] = vo;
+    finish_particle(i, pi, vi, gx.x + gx.y, gy.x + gy.y, a.ph.pair_scale, a.ph.pair_scale_y, a);
 }
 
 template <int KN, int FRAC, bool ANISO>
@@ -412,6 +418,8 @@ __global__ void __launch_bounds__(kTile, 8) step_kernel(const StepArgs a) {
         step_particle<KN, FRAC, ANISO>(i, pi, vi, cell, cs, zero, pp, zero, a);
     }
 }
+
+#include "step_float.cuh"
 
 // ------------------------------------------------------------------------------------------------
 // Binning: stable counting sort by cell (count -> scan -> scatter -> order fix-up + gather).
@@ -487,6 +495,13 @@ __global__ void key_count_kernel(Source src, Grid g, uint32_t* __restrict__ cell
     rank[c] = atomicAdd(&cell_count[key], 1u);
 }
 
+// PAD: scan the counts rounded up to even (pad_start of the fp32 step kernel) instead of the counts.
+template <bool PAD>
+__device__ __forceinline__ uint32_t scan_item(uint32_t v) {
+    return PAD ? (v + 1u) & ~1u : v;
+}
+
+template <bool PAD>
 __global__ void __launch_bounds__(kScanThreads) scan_reduce_kernel(const uint32_t* __restrict__ in, uint32_t count,
                                                                    uint32_t* __restrict__ block_sum) {
     __shared__ uint32_t warp_sum[kScanThreads / 32];
@@ -494,7 +509,7 @@ __global__ void __launch_bounds__(kScanThreads) scan_reduce_kernel(const uint32_
     uint32_t v = 0;
 #pragma unroll
     for (int k = 0; k < kScanItems; ++k)
-        if (base + k < count) v += in[base + k];
+        if (base + k < count) v += scan_item<PAD>(in[base + k]);
     for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xFFFFFFFFu, v, o);
     if ((threadIdx.x & 31) == 0) warp_sum[threadIdx.x >> 5] = v;
     __syncthreads();
@@ -540,6 +555,7 @@ __global__ void __launch_bounds__(1024) scan_top_kernel(uint32_t* __restrict__ b
     if (threadIdx.x == 0) *total_out = carry;
 }
 
+template <bool PAD>
 __global__ void __launch_bounds__(kScanThreads) scan_apply_kernel(const uint32_t* __restrict__ in, uint32_t count,
                                                                   const uint32_t* __restrict__ block_offset,
                                                                   uint32_t* __restrict__ out) {
@@ -549,7 +565,7 @@ __global__ void __launch_bounds__(kScanThreads) scan_apply_kernel(const uint32_t
     uint32_t t = 0;
 #pragma unroll
     for (int k = 0; k < kScanItems; ++k) {
-        v[k] = base + k < count ? in[base + k] : 0;
+        v[k] = base + k < count ? scan_item<PAD>(in[base + k]) : 0;
         t += v[k];
     }
     uint32_t incl = t;
@@ -609,10 +625,12 @@ __global__ void gather_kernel(Source src, uint32_t p_lo, uint32_t p_hi, Grid g,
 
 // The few numbers the host needs after a binning: where the owned rows and their two boundary rows
 // start and end in the sorted arrays. out[0] = own_lo, [1] = end of the first owned row,
-// [2] = start of the last owned row, [3] = own_hi, [4] = total (with ghost rows), [5] = error flags.
+// [2] = start of the last owned row, [3] = own_hi, [4] = total (with ghost rows), [5] = error flags,
+// [6] = tiles of step_kernel_c.
 __global__ void slab_counts_kernel(const uint32_t* __restrict__ cell_start, Grid g, const uint32_t* __restrict__ flags,
-                                   uint32_t* __restrict__ out) {
+                                   const uint32_t* __restrict__ couple_tiles, uint32_t* __restrict__ out) {
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    out[6] = couple_tiles ? *couple_tiles : 0u;  // tiles of step_kernel_c (step_float.cuh)
     out[0] = cell_start[g.own_row0 * g.bx];
     out[1] = cell_start[(g.own_row0 + 1) * g.bx];
     out[2] = cell_start[(g.own_row0 + g.own_rows - 1) * g.bx];
@@ -816,6 +834,17 @@ struct PsimStepper {
     uint32_t* cell_id = nullptr;
     TileDesc* tiles = nullptr;
     uint32_t* cell_start = nullptr;  // cells + 1 (+ padding)
+    uint32_t* pad_start = nullptr;   // cells + 1: prefix sum of the cell counts rounded up to even (step_float.cuh)
+    uint32_t* couple_i0 = nullptr;   // per couple: first particle | has-a-second << 31
+    uint32_t* tile_base = nullptr;   // own_rows + 1: first tile of every owned row
+    uint32_t* d_couple_tiles = nullptr;
+    TileC* tiles_c = nullptr;
+    uint32_t* col_start = nullptr;   // tiles_c_cap x kColStride: band slot of every column of every tile
+    uint32_t tiles_c_cap = 0, n_tiles_c = 0;
+    bool float_grid = false;         // the grid is fine enough for step_kernel_c's exact fp32 offsets
+    bool float_path = false;         // ... and the metadata's physics has a step_kernel_c variant
+    PhysF physf{};
+    bool force_int_path = false;     // PSIM_FORCE_INT_PATH=1: step_kernel on every grid (A/B measurements, tests)
     uint32_t* cell_count = nullptr;  // cells
     uint32_t* block_sum = nullptr;
     uint32_t* rank_in_cell = nullptr;
@@ -1019,9 +1048,49 @@ Phys make_phys(const FrameMetadata& m, int* kernel_kn, int* kernel_frac, bool* a
     return ph;
 }
 
+// Constants of step_kernel_c (step_float.cuh). Returns false when these physics / this grid have no fp32 variant.
+bool make_phys_f(const FrameMetadata& m, const Phys& ph, const Grid& g, int kn, int frac, PhysF* out) {
+    if (kn == 0 || frac == kFracEx2) return false;  // run-time exponents, MUFU.EX2 sliver: step_kernel only
+    int ye;
+    if (std::frexp((double)ph.yscale, &ye) != 0.5) return false;  // ky/kx must fold into a power-of-two scale
+    const MiePotentialParams& p = m.particles[0];
+    PhysF pf{};
+    // kx / sigma = f * 2^ex with f in [1, 2): offsets are scaled by 2^ex, f goes into the constants
+    int ex;
+    const double inv_c = (double)ph.kx / (double)p.sigma;
+    const double f = 2.0 * std::frexp(inv_c, &ex);
+    ex -= 1;
+    pf.sx = (float)std::ldexp(1.0, ex);
+    pf.sy = pf.sx * ph.yscale;
+    pf.sxbits = g.sx;
+    pf.zl = g.sx <= 21 ? 2 : 1;
+    const uint32_t stride = 1u << pf.zl;
+    pf.half_span = (stride + 2u) << (g.sx - 1);
+    pf.zone_shift = (float)std::ldexp((double)stride, (int)g.sx + ex);
+    // scaled r^2 = true (r/sigma)^2 / f^2, so with qs = 1/scaled r^2 = q f^2:
+    //   g f^(2 km) = qs^km - (n/m) f^(-2(kn-km)) qs^kn q^fn ,   q^fn = 2^z,  z = fn log2 q = -fn (l + 2 log2 f)
+    const double km = ph.km, knd = ph.kn, fn = ph.fn;
+    const double Kc = (double)ph.nm * std::pow(f, -2.0 * (knd - km));
+    if (frac == kFracNone) {
+        pf.d0 = (float)-Kc;
+    } else {
+        const double c1 = ph.c1, c2 = ph.c2, c3 = ph.c3;  // 2^z ~ 1 + z (c1 + z (c2 + z c3)), fitted by make_phys
+        const double a = -fn, b = -2.0 * fn * std::log2(f);
+        pf.d0 = (float)(-Kc * (1.0 + b * (c1 + b * (c2 + b * c3))));
+        pf.d1 = (float)(-Kc * a * (c1 + b * (2.0 * c2 + 3.0 * c3 * b)));
+        pf.d2 = (float)(-Kc * a * a * (c2 + 3.0 * c3 * b));
+        pf.d3 = (float)(-Kc * a * a * a * c3);
+    }
+    pf.pair_scale = (float)((double)ph.pair_scale * std::pow(f, -2.0 * km) / (double)pf.sx);
+    *out = pf;
+    return true;
+}
+
 void apply_metadata(PsimStepper* s, const FrameMetadata& m) {
     s->meta = m;
     s->phys = make_phys(m, &s->kernel_kn, &s->kernel_frac, &s->kernel_aniso);
+    s->float_path = s->float_grid && !s->force_int_path &&
+                    make_phys_f(m, s->phys, s->grid, s->kernel_kn, s->kernel_frac, &s->physf);
 }
 
 template <int KN, int FRAC>
@@ -1039,7 +1108,29 @@ void launch_step_frac(PsimStepper* s, const StepArgs& a, uint32_t tiles) {
     }
 }
 
+template <int KN>
+void launch_step_c(PsimStepper* s, const StepArgs& a) {
+    StepArgsC ac;
+    ac.couple_i0 = s->couple_i0;
+    ac.tiles = s->tiles_c;
+    ac.col_start = s->col_start;
+    ac.pf = s->physf;
+    if (s->kernel_frac == kFracNone) step_kernel_c<KN, kFracNone><<<s->n_tiles_c, kCouples, 0, s->stream>>>(a, ac);
+    else step_kernel_c<KN, kFracPoly><<<s->n_tiles_c, kCouples, 0, s->stream>>>(a, ac);
+}
+
 void launch_step(PsimStepper* s, const StepArgs& a, uint32_t tiles) {
+    if (s->float_path) {
+        switch (s->kernel_kn) {
+            case 5: launch_step_c<5>(s, a); break;
+            case 6: launch_step_c<6>(s, a); break;
+            case 7: launch_step_c<7>(s, a); break;
+            case 8: launch_step_c<8>(s, a); break;
+            case 9: launch_step_c<9>(s, a); break;
+            default: launch_step_c<10>(s, a); break;
+        }
+        return;
+    }
     switch (s->kernel_kn) {
         case 5: launch_step_frac<5>(s, a, tiles); break;
         case 6: launch_step_frac<6>(s, a, tiles); break;
@@ -1177,10 +1268,18 @@ XferOp ghost_positions_op(PsimStepper* s) {
 int enqueue_scan(PsimStepper* s) {
     uint32_t cells = s->grid.cells;
     uint32_t blocks = div_up(cells, kScanBlock);
-    scan_reduce_kernel<<<blocks, kScanThreads, 0, s->stream>>>(s->cell_count, cells, s->block_sum);
+    scan_reduce_kernel<false><<<blocks, kScanThreads, 0, s->stream>>>(s->cell_count, cells, s->block_sum);
     scan_top_kernel<<<1, 1024, 0, s->stream>>>(s->block_sum, blocks, s->cell_start + cells);
-    scan_apply_kernel<<<blocks, kScanThreads, 0, s->stream>>>(s->cell_count, cells, s->block_sum, s->cell_start);
+    scan_apply_kernel<false><<<blocks, kScanThreads, 0, s->stream>>>(s->cell_count, cells, s->block_sum, s->cell_start);
     s->launches += 3;
+    if (s->float_grid) {  // pad_start: the same scan over the counts rounded up to even (step_float.cuh)
+        scan_reduce_kernel<true><<<blocks, kScanThreads, 0, s->stream>>>(s->cell_count, cells, s->block_sum);
+        scan_top_kernel<<<1, 1024, 0, s->stream>>>(s->block_sum, blocks, s->pad_start + cells);
+        scan_apply_kernel<true><<<blocks, kScanThreads, 0, s->stream>>>(s->cell_count, cells, s->block_sum, s->pad_start);
+        couple_build_kernel<<<div_up(cells, 256), 256, 0, s->stream>>>(s->cell_start, s->pad_start, cells, s->couple_i0);
+        row_tiles_kernel<<<1, 1024, 0, s->stream>>>(s->pad_start, s->grid, s->tile_base, s->d_couple_tiles);
+        s->launches += 5;
+    }
     CK(cudaGetLastError());
     return PSIM_OK;
 }
@@ -1248,7 +1347,7 @@ int bin_phase_scan(PsimStepper* s, bool need_counts) {
     int rc = enqueue_scan(s);
     if (rc) return rc;
     if (need_counts) {
-        slab_counts_kernel<<<1, 32, 0, s->stream>>>(s->cell_start, s->grid, s->d_flags, s->d_counts);
+        slab_counts_kernel<<<1, 32, 0, s->stream>>>(s->cell_start, s->grid, s->d_flags, s->d_couple_tiles, s->d_counts);
         s->launches += 1;
         CK(cudaGetLastError());
         CK(cudaMemcpyAsync(s->h_counts, s->d_counts, 8 * sizeof(uint32_t), cudaMemcpyDeviceToHost, s->stream));
@@ -1278,6 +1377,11 @@ int bin_phase_commit(PsimStepper* s) {
     s->own_hi = h[3];
     s->n_total = h[4];
     s->n = owned;
+    if (s->float_grid) {
+        if (h[6] > s->tiles_c_cap)
+            return fail(s, PSIM_ECAPACITY, "internal: %u couple tiles, room for %u", h[6], s->tiles_c_cap);
+        s->n_tiles_c = h[6];
+    }
     return PSIM_OK;
 }
 
@@ -1308,6 +1412,12 @@ int bin_phase_tiles(PsimStepper* s) {
     if (tiles == 0) return PSIM_OK;
     tile_desc_kernel<<<div_up(tiles, 128), 128, 0, s->stream>>>(s->cell_start, s->grid, s->own_lo, s->own_hi, s->tiles);
     s->launches += 1;
+    if (s->float_grid && s->n_tiles_c) {
+        tile_build_kernel<<<div_up(s->n_tiles_c, 128), 128, 0, s->stream>>>(s->cell_start, s->pad_start, s->tile_base,
+                                                                          s->couple_i0, s->cell_id, s->grid, s->tiles_c,
+                                                                          s->col_start);
+        s->launches += 1;
+    }
     CK(cudaGetLastError());
     return PSIM_OK;
 }
@@ -1354,7 +1464,7 @@ int team_bin(const Team& t, bool ingest, const Particle* records, uint32_t count
         if ((rc = bin_phase_count(s, src, ops[r]))) return rc;
     }
     if ((rc = team_exchange(t, ops))) return rc;
-    const bool need_counts = ingest || slabs;
+    const bool need_counts = ingest || slabs || t.ranks[0]->float_grid;  // the couple tiles are counted on the device
     for (int r = 0; r < t.count; ++r)
         if ((rc = bin_phase_scan(t.ranks[r], need_counts))) return rc;
     if (need_counts) {
@@ -1608,6 +1718,12 @@ void psim_destroy(PsimStepper* s) {
         cudaFree(s->mig_idx[k]);
     }
     cudaFree(s->cell_start);
+    cudaFree(s->pad_start);
+    cudaFree(s->couple_i0);
+    cudaFree(s->tile_base);
+    cudaFree(s->d_couple_tiles);
+    cudaFree(s->tiles_c);
+    cudaFree(s->col_start);
     cudaFree(s->cell_count);
     cudaFree(s->block_sum);
     cudaFree(s->rank_in_cell);
@@ -1667,6 +1783,7 @@ int psim_create(const PsimConfig* config, PsimStepper** out) {
     st->cfg.slab_count = nranks;
     if (st->cfg.rebin_every == 0) st->cfg.rebin_every = 17;
     st->device = device;
+    if (const char* env = getenv("PSIM_FORCE_INT_PATH")) st->force_int_path = env[0] == '1';
     st->rank = (int)config->slab_rank;
     st->nranks = (int)nranks;
     Grid& g = st->grid;
@@ -1722,6 +1839,20 @@ int psim_create(const PsimConfig* config, PsimStepper** out) {
         }
     }
     CKC(cudaMalloc(&st->cell_start, sizeof(uint32_t) * ((size_t)g.cells + 1 + kPadCells)));
+    // step_kernel_c needs cells of at most 2^22 fixed-point units (exact fp32 offsets within a zone / a tile's rows)
+    st->float_grid = g.sx <= 22 && g.sy <= 22;
+    if (st->float_grid) {
+        // couples: every particle, plus one half-empty couple per cell at most
+        const size_t couples = (cap_total + std::min<size_t>(cap_total, g.cells)) / 2 + 1;
+        st->tiles_c_cap = (uint32_t)((cap + std::min<size_t>(cap, (size_t)g.own_rows * g.bx)) / 2 / kCouples + g.own_rows + 1);
+        CKC(cudaMalloc(&st->pad_start, sizeof(uint32_t) * ((size_t)g.cells + 1 + kPadCells)));
+        CKC(cudaMemset(st->pad_start, 0, sizeof(uint32_t) * ((size_t)g.cells + 1 + kPadCells)));
+        CKC(cudaMalloc(&st->couple_i0, sizeof(uint32_t) * couples));
+        CKC(cudaMalloc(&st->tile_base, sizeof(uint32_t) * ((size_t)g.own_rows + 1)));
+        CKC(cudaMalloc(&st->d_couple_tiles, sizeof(uint32_t)));
+        CKC(cudaMalloc(&st->tiles_c, sizeof(TileC) * (size_t)st->tiles_c_cap));
+        CKC(cudaMalloc(&st->col_start, sizeof(uint32_t) * kColStride * (size_t)st->tiles_c_cap));
+    }
     CKC(cudaMalloc(&st->cell_count, sizeof(uint32_t) * (size_t)g.cells));
     CKC(cudaMalloc(&st->block_sum, sizeof(uint32_t) * (size_t)div_up(g.cells, kScanBlock)));
     CKC(cudaMalloc(&st->rank_in_cell, sizeof(uint32_t) * cand_cap));
@@ -1919,6 +2050,37 @@ int psim_get_step_timing(PsimStepper* s, double* total_ms, uint64_t* launches) {
     return PSIM_OK;
 }
 
+int psim_tile_stats(PsimStepper* s, PsimTileStats* out) {
+    if (!s || !out) return PSIM_EINVAL;
+    std::memset(out, 0, sizeof *out);
+    CK(cudaSetDevice(s->device));
+    CK(cudaStreamSynchronize(s->stream));
+    out->float_path = s->float_path ? 1u : 0u;
+    if (s->float_path) {
+        std::vector<TileC> t(s->n_tiles_c);
+        if (!t.empty()) CK(cudaMemcpy(t.data(), s->tiles_c, sizeof(TileC) * t.size(), cudaMemcpyDeviceToHost));
+        out->tiles = s->n_tiles_c;
+        for (const TileC& x : t) {
+            out->tiles_staged += x.fits ? 1u : 0u;
+            out->threads_live += x.nk;
+            out->max_columns = std::max(out->max_columns, x.ncol);
+        }
+        out->threads_launched = (uint64_t)s->n_tiles_c * kCouples;
+    } else {
+        std::vector<TileDesc> t(div_up(s->n, kTile));
+        if (!t.empty()) CK(cudaMemcpy(t.data(), s->tiles, sizeof(TileDesc) * t.size(), cudaMemcpyDeviceToHost));
+        out->tiles = (uint32_t)t.size();
+        for (const TileDesc& x : t) {
+            out->tiles_staged += x.fits ? 1u : 0u;
+            out->max_columns = std::max(out->max_columns, x.last - x.first + 3);
+            for (int d = 0; d < 3; ++d) out->max_row_particles = std::max(out->max_row_particles, x.p_cnt[d]);
+        }
+        out->threads_live = s->n;
+        out->threads_launched = (uint64_t)t.size() * kTile;
+    }
+    return PSIM_OK;
+}
+
 int psim_device_state(PsimStepper* s, const void** pos, const void** vel, const void** ty, const void** cell_start) {
     if (!s) return PSIM_EINVAL;
     if (pos) *pos = s->pos[s->cur_pos] + s->own_lo;
@@ -1958,9 +2120,10 @@ int psim_group_create(PsimStepper* const* steppers, uint32_t count, PsimGroup** 
         if (!m || m->group || m->comm || m->nranks != (int)count || m->rank != (int)r ||
             m->device != steppers[0]->device || m->cfg.grid_x_log2 != steppers[0]->cfg.grid_x_log2 ||
             m->cfg.grid_y_log2 != steppers[0]->cfg.grid_y_log2 || m->cfg.schedule != steppers[0]->cfg.schedule ||
-            m->cfg.rebin_every != steppers[0]->cfg.rebin_every || m->box_capacity != steppers[0]->box_capacity)
+            m->cfg.rebin_every != steppers[0]->cfg.rebin_every || m->box_capacity != steppers[0]->box_capacity ||
+            m->ingest_cap != steppers[0]->ingest_cap)  // every slab scans the whole ingested frame
             return fail(s, PSIM_EINVAL, "psim_group_create: stepper %u must be slab %u of %u on the group's device "
-                        "with the group's grid, schedule and capacities", r, r, count);
+                        "with the group's grid, schedule and capacities (ingest_capacity included)", r, r, count);
     }
     CK(cudaSetDevice(steppers[0]->device));
     PsimGroup* g = new PsimGroup;

@@ -55,6 +55,12 @@ class CSlabInfo(ctypes.Structure):
         "ghost_below", "ghost_above", "ghost_capacity", "migrant_capacity")] + [("_reserved", ctypes.c_uint32 * 5)]
 
 
+class CTileStats(ctypes.Structure):
+    _fields_ = [(n, ctypes.c_uint32) for n in ("float_path", "tiles", "tiles_staged", "max_columns",
+                                               "max_row_particles", "_reserved")] + \
+               [("threads_live", ctypes.c_uint64), ("threads_launched", ctypes.c_uint64)]
+
+
 def lib() -> ctypes.CDLL:
     """Load libpsim_b200.so; raises if it has not been built (the product has no other path)."""
     global _lib
@@ -90,6 +96,7 @@ def lib() -> ctypes.CDLL:
             "psim_get_step_timing": [vp, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_uint64)],
             "psim_device_state": [vp, ctypes.POINTER(vp), ctypes.POINTER(vp), ctypes.POINTER(vp), ctypes.POINTER(vp)],
             "psim_slab_info": [vp, ctypes.POINTER(CSlabInfo)],
+            "psim_tile_stats": [vp, ctypes.POINTER(CTileStats)],
             "psim_comm_unique_id": [vp],
             "psim_comm_init": [vp, vp],
             "psim_group_create": [ctypes.POINTER(vp), ctypes.c_uint32, ctypes.POINTER(vp)],
@@ -228,6 +235,11 @@ class Stepper:
         self._check(lib().psim_slab_info(self._h, ctypes.byref(info)))
         return {n: int(getattr(info, n)) for n, _ in CSlabInfo._fields_ if n != "_reserved"}
 
+    def tile_stats(self) -> dict:
+        st = CTileStats()
+        self._check(lib().psim_tile_stats(self._h, ctypes.byref(st)))
+        return {n: int(getattr(st, n)) for n, _ in CTileStats._fields_ if n != "_reserved"}
+
     # -- introspection -----------------------------------------------------------------------
     @property
     def particle_count(self) -> int:
@@ -273,7 +285,7 @@ class SlabGroup:
                  ghost_capacity: int = 0, migrant_capacity: int = 0):
         self.slabs = [Stepper(grid_log2, max_particles_per_slab, schedule, rebin_every, device, slab_rank=r,
                               slab_count=slab_count, ghost_capacity=ghost_capacity,
-                              migrant_capacity=migrant_capacity, ingest_capacity=ingest_capacity if r == 0 else 0)
+                              migrant_capacity=migrant_capacity, ingest_capacity=ingest_capacity)
                       for r in range(slab_count)]
         arr = (ctypes.c_void_p * slab_count)(*[s._h for s in self.slabs])
         self._g = ctypes.c_void_p()
