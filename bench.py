@@ -225,6 +225,8 @@ def run_ours(args, rank: int, world: int, local_rank: int) -> None:
         st = Stepper(wl.grid_log2, int(1.05 * 3162 * 3163), device=local_rank, slab_rank=rank, slab_count=world,
                      ingest_capacity=wl.frame.count)
         st.comm_init(uid)
+    halo = {0: "none (single slab)", 1: "ncclSend/ncclRecv after every step",
+            2: "pushed by the step kernel over NVLink peer memory (CUDA IPC), epoch flags"}[st.halo_mode]
     wl.frame.metadata["steps_per_frame"] = STEPS_PER_FRAME
     executed = schedule_steps(STEPS_PER_FRAME)
     st.set_stream(stream.cuda_stream)
@@ -299,8 +301,9 @@ def run_ours(args, rank: int, world: int, local_rank: int) -> None:
                        "l2": "state (10M x 20 B x 2 buffers = 400 MB per GPU) is larger than the 126 MB L2; "
                              "no flush",
                        "decomposition": "single slab" if world == 1 else
-                       f"{world} slabs of 2048 cell rows, one per GPU; per step: NCCL send/recv of the two "
-                       "boundary rows' positions; per re-bin: migrants + boundary-row cell counts"},
+                       f"{world} slabs of 2048 cell rows, one per GPU; halo (boundary rows' positions) every step: "
+                       f"{halo}; per re-bin: migrants + boundary-row cell counts + fresh ghost rows by ncclSend/ncclRecv",
+                       "step_kernel": st.tile_stats()},
             "roofline": {"bound": "hbm", "kernel": "step_kernel (fused 3x3-cell force + kick + drift)",
                          "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "peak_source": peak_src, "traffic": recorded_traffic(),

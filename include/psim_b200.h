@@ -161,7 +161,15 @@ int psim_device_state(PsimStepper* s, const void** pos, const void** vel, const 
  * frames concatenated in rank order are the single-slab frame.
  * NCCL (libnccl.so.2, or $PSIM_NCCL_LIB) is loaded on first use; a single-slab user never needs it. */
 int psim_comm_unique_id(void* out128);                         /* rank 0: ncclGetUniqueId, 128 bytes    */
-int psim_comm_init(PsimStepper* s, const void* unique_id128);  /* all ranks: ncclCommInitRank           */
+/* All ranks: ncclCommInitRank, then the slabs exchange CUDA IPC handles of their position buffers. When every
+ * rank could map its neighbours (same node, peer access over NVLink), the per-step halo exchange needs no
+ * collective call at all: the step kernel stores the new positions of its boundary rows straight into the
+ * neighbours' ghost rows and publishes an epoch word; only the neighbours' boundary tiles wait for it.
+ * Otherwise (or with PSIM_HALO=nccl) every step is followed by an ncclSend/ncclRecv pair per neighbour.
+ * Re-binning (migrants, ghost-row cell counts, fresh ghost rows) always uses ncclSend/ncclRecv. */
+int psim_comm_init(PsimStepper* s, const void* unique_id128);
+/* 0: single slab, 1: halo by send/recv after every step, 2: halo pushed by the step kernel over peer memory. */
+int psim_halo_mode(const PsimStepper* s);
 
 /* ---- slab decomposition inside one process on one device ----------------------------------------
  * The same slabs, exchanges done by device-to-device copies on one stream. It validates the

@@ -116,6 +116,13 @@ __global__ void __launch_bounds__(kCouples, 9) step_kernel_c(const StepArgs a, c
     const TileC t = ac.tiles[blockIdx.x];
     const bool live = threadIdx.x < t.nk;
 
+    if (a.push) {  // uniform over the grid
+        if (threadIdx.x == 0) {
+            if (blockIdx.x == 0) halo_publish_empty(a);
+            halo_wait(a, blockIdx.x);
+        }
+        if (!t.fits) __syncthreads();  // the global-memory path reads the ghost rows directly
+    }
     if (!t.fits) {  // very sparse or very crowded spot: same physics straight from global memory, one particle at a time
         if (!live) return;
         const uint32_t w = ac.couple_i0[t.k0 + threadIdx.x];
@@ -124,7 +131,7 @@ __global__ void __launch_bounds__(kCouples, 9) step_kernel_c(const StepArgs a, c
         const uint2* pp[3] = {a.pos_in, a.pos_in, a.pos_in};
         const uint32_t zero[3] = {0, 0, 0};
         for (uint32_t i = i0; i <= i0 + (w >> 31); ++i)
-            step_particle<KN, FRAC, true>(i, a.pos_in[i], a.vel[i], a.cell_id[i], cs, zero, pp, zero, a);
+            step_particle<KN, FRAC, true, true>(i, a.pos_in[i], a.vel[i], a.cell_id[i], cs, zero, pp, zero, a);
         return;
     }
 
@@ -187,7 +194,7 @@ __global__ void __launch_bounds__(kCouples, 9) step_kernel_c(const StepArgs a, c
         float4* out = s_nb + dst;
 #pragma unroll 1
         for (uint32_t k = 0; k < r1 - r0; ++k) {
-            const uint2 p = src[k];
+            const uint2 p = __ldcg(src + k);  // L2: a ghost row is written by the neighbour while this kernel runs
             const float xe = __int2float_rn((int)(p.x - xo0)) * pf.sx;
             const float y = __int2float_rn((int)(p.y - t.yc)) * pf.sy;
             out[k] = make_float4(xe, y, xe + to_odd, y);

@@ -245,13 +245,21 @@ __device__ __forceinline__ void pair2(uint2 pi, uint2 pj0, uint2 pj1, const Phys
 }
 
 // All of one window [0, count) of staged neighbours, two at a time, in ascending index order.
-template <int KN, int FRAC, bool ANISO, bool CLAMP>
+// CG: the window lies in global memory; loads go to L2 (a ghost row is written by the neighbour slab while
+// this kernel runs, and another tile on this SM may have pulled a stale copy of its sector into L1).
+template <bool CG>
+__device__ __forceinline__ uint2 load_pos(const uint2* p) {
+    return CG ? __ldcg(p) : *p;
+}
+
+template <int KN, int FRAC, bool ANISO, bool CLAMP, bool CG>
 __device__ __forceinline__ void window_accumulate(const uint2* __restrict__ pj, int count, uint2 pi, const Phys& ph,
                                                   float2& gx, float2& gy) {
     int k = 0;
 #pragma unroll 2
-    for (; k + 1 < count; k += 2) pair2<KN, FRAC, ANISO, false, CLAMP>(pi, pj[k], pj[k + 1], ph, gx, gy);
-    if (k < count) pair2<KN, FRAC, ANISO, true, CLAMP>(pi, pj[k], pi, ph, gx, gy);
+    for (; k + 1 < count; k += 2)
+        pair2<KN, FRAC, ANISO, false, CLAMP>(pi, load_pos<CG>(pj + k), load_pos<CG>(pj + k + 1), ph, gx, gy);
+    if (k < count) pair2<KN, FRAC, ANISO, true, CLAMP>(pi, load_pos<CG>(pj + k), pi, ph, gx, gy);
 }
 
 // Repulsive wall term C eps m (sigma/d)^m / d (particle.cuh:68-71).
@@ -324,6 +332,57 @@ __device__ __forceinline__ int last_le(const uint32_t* a, int count, uint32_t i)
 // the same code with the pointers aimed at global memory instead.
 // ------------------------------------------------------------------------------------------------
 
+// ------------------------------------------------------------------------------------------------
+// Halo exchange inside the step kernel (slab decomposition).
+//
+// Each slab keeps one ghost row of each neighbour. Instead of a send/recv after every step, the threads
+// that step a particle of a boundary row store its new position twice: in the slab's own array and, through
+// peer-mapped memory (NVLink P2P: CUDA IPC between processes, plain pointers inside one process), in the
+// neighbour's ghost row of the buffer the neighbour's NEXT step reads. Synchronisation is one epoch word
+// per direction in the receiver's HaloHeader:
+//   * the thread that pushes the last particle of a boundary row publishes this step's epoch
+//     (__threadfence_system + store to the neighbour's header);
+//   * only the CTAs that read a ghost row (the tiles of the first / last owned row -- the same CTAs that
+//     produce the outgoing halo) wait, before staging, until the neighbour has published the previous
+//     step's epoch. Interior tiles never wait, so the transfer overlaps the interior's pair loops.
+// That wait also covers the write-after-read hazard: a neighbour publishes epoch k only after ITS
+// boundary tiles of step k have finished, i.e. have finished reading the ghost rows step k+1 overwrites.
+// Boundary tiles come first / last in the grid, so their halo is on the wire while the interior computes.
+// ------------------------------------------------------------------------------------------------
+struct HaloHeader {     // one per slab, in device memory its two neighbours can reach
+    uint32_t flags[2];  // [0]: last epoch published by the lower neighbour, [1]: by the upper one
+    uint32_t done[2];   // boundary particles pushed so far in the running step, per side
+    uint32_t own_hi;    // where this slab's upper ghost row starts (written at every binning)
+    uint32_t error;     // sticky: a wait timed out (the neighbour died); waits stop blocking
+    uint32_t _pad[2];
+};
+
+struct HaloArgs {
+    uint2* peer_out[2];       // the neighbour's position buffer this step writes ([0] lower, [1] upper); null: none
+    HaloHeader* peer_hdr[2];
+    HaloHeader* hdr;
+    uint32_t lo_end, hi_start;    // [own_lo, lo_end) goes to the lower neighbour, [hi_start, own_hi) to the upper one
+    uint32_t lo_tiles, hi_tile0;  // the tiles that hold (and read the ghost row next to) them: [0, lo_tiles), [hi_tile0, ..)
+    uint32_t wait_epoch[2];       // 0: the ghost row is already in place (a binning delivered it)
+    uint32_t pub_epoch;
+};
+
+constexpr unsigned long long kHaloTimeoutNs = 20ull * 1000 * 1000 * 1000;
+
+__device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
+    uint32_t v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v) {
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long global_timer_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+
 struct StepArgs {
     const uint2* __restrict__ pos_in;
     uint2* __restrict__ pos_out;
@@ -334,7 +393,61 @@ struct StepArgs {
     uint32_t own_lo, own_hi;  // the particles this stepper steps: [own_lo, own_hi) (ghost rows lie outside)
     Grid g;
     Phys ph;
+    uint32_t push;  // 1: boundary rows are pushed into the neighbours' ghost rows by this kernel (HaloArgs)
+    HaloArgs h;
 };
+
+// Before a tile that reads a ghost row stages anything: wait for the neighbour's previous step (one thread).
+__device__ __forceinline__ void halo_wait(const StepArgs& a, uint32_t tile) {
+    const HaloArgs& h = a.h;
+#pragma unroll
+    for (int side = 0; side < 2; ++side) {
+        const bool reads_ghost = side == 0 ? tile < h.lo_tiles : tile >= h.hi_tile0;
+        if (!h.peer_out[side] || !h.wait_epoch[side] || !reads_ghost) continue;
+        if (ld_acquire_sys(&h.hdr->error)) continue;
+        const unsigned long long t0 = global_timer_ns();
+        while ((int32_t)(ld_acquire_sys(&h.hdr->flags[side]) - h.wait_epoch[side]) < 0) {
+            if (global_timer_ns() - t0 > kHaloTimeoutNs) {
+                st_release_sys(&h.hdr->error, 1u);
+                break;
+            }
+        }
+    }
+}
+
+__device__ __forceinline__ void halo_publish(const HaloArgs& h, int side) {
+    h.hdr->done[side] = 0;  // for the next step (its launch is ordered after this kernel)
+    __threadfence_system();
+    st_release_sys(&h.peer_hdr[side]->flags[side ^ 1], h.pub_epoch);
+}
+
+// A boundary row without particles has nobody to publish its epoch: the first thread of the grid does.
+__device__ __forceinline__ void halo_publish_empty(const StepArgs& a) {
+    const HaloArgs& h = a.h;
+    if (h.peer_out[0] && h.lo_end == a.own_lo) halo_publish(h, 0);
+    if (h.peer_out[1] && h.hi_start == a.own_hi) halo_publish(h, 1);
+}
+
+// The new position of boundary-row particle i also goes into the neighbour's ghost row.
+__device__ __forceinline__ void halo_push(const StepArgs& a, uint32_t i, uint2 po) {
+    const HaloArgs& h = a.h;
+    if (h.peer_out[0] && i < h.lo_end) {
+        const uint32_t base = ld_acquire_sys(&h.peer_hdr[0]->own_hi);  // the lower slab's upper ghost row
+        h.peer_out[0][base + (i - a.own_lo)] = po;
+        __threadfence_system();
+        if (atomicAdd(&h.hdr->done[0], 1u) + 1u == h.lo_end - a.own_lo) halo_publish(h, 0);
+    }
+    if (h.peer_out[1] && i >= h.hi_start) {
+        h.peer_out[1][i - h.hi_start] = po;  // the upper slab's lower ghost row starts at 0
+        __threadfence_system();
+        if (atomicAdd(&h.hdr->done[1], 1u) + 1u == a.own_hi - h.hi_start) halo_publish(h, 1);
+    }
+}
+
+// A slab without particles still owes its neighbours the epoch of every step.
+__global__ void halo_publish_kernel(StepArgs a) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) halo_publish_empty(a);
+}
 
 // Cursor + wall force, pair sum, kick + drift and the two stores of one particle (shared by all step kernels).
 __device__ __forceinline__ void finish_particle(uint32_t i, uint2 pi, float2 vi, float sum_x, float sum_y,
@@ -347,9 +460,10 @@ __device__ __forceinline__ void finish_particle(uint32_t i, uint2 pi, float2 vi,
     integrate(pi, vi, f, a.ph, po, vo);
     a.pos_out[i] = po;
     a.vel[i] = vo;
+    if (a.push) halo_push(a, i, po);
 }
 
-template <int KN, int FRAC, bool ANISO>
+template <int KN, int FRAC, bool ANISO, bool CG>
 __device__ __forceinline__ void step_particle(uint32_t i, uint2 pi, float2 vi, uint32_t cell,
                                               const uint32_t* const cs[3], const uint32_t cs_lo[3],
                                               const uint2* const pp[3], const uint32_t pp_lo[3], const StepArgs& a) {
@@ -364,8 +478,8 @@ __device__ __forceinline__ void step_particle(uint32_t i, uint2 pi, float2 vi, u
         uint32_t c0 = ((uint32_t)row << g.lx) + x0, c1 = ((uint32_t)row << g.lx) + x1;
         uint32_t s = cs[d][c0 - cs_lo[d]], e = cs[d][c1 + 1 - cs_lo[d]];
         const uint2* win = pp[d] + (s - pp_lo[d]);  // window [s, e) of this row
-        if (d == 1) window_accumulate<KN, FRAC, ANISO, true>(win, (int)(e - s), pi, a.ph, gx, gy);  // contains i
-        else window_accumulate<KN, FRAC, ANISO, false>(win, (int)(e - s), pi, a.ph, gx, gy);
+        if (d == 1) window_accumulate<KN, FRAC, ANISO, true, CG>(win, (int)(e - s), pi, a.ph, gx, gy);  // contains i
+        else window_accumulate<KN, FRAC, ANISO, false, CG>(win, (int)(e - s), pi, a.ph, gx, gy);
     }
     finish_particle(i, pi, vi, gx.x + gx.y, gy.x + gy.y, a.ph.pair_scale, a.ph.pair_scale_y, a);
 }
@@ -380,6 +494,13 @@ __global__ void __launch_bounds__(kTile, 8) step_kernel(const StepArgs a) {
     const uint32_t i = a.own_lo + b * kTile + threadIdx.x;
     const TileDesc t = a.tiles[b];
 
+    if (a.push) {  // uniform over the grid
+        if (threadIdx.x == 0) {
+            if (b == 0) halo_publish_empty(a);
+            halo_wait(a, b);
+        }
+        if (!t.fits) __syncthreads();  // the global-memory path reads the ghost rows directly
+    }
     if (t.fits) {
         if (threadIdx.x == 0) {
             mbar_init(&s_bar, 1);
@@ -409,13 +530,13 @@ __global__ void __launch_bounds__(kTile, 8) step_kernel(const StepArgs a) {
         if (!live) return;
         const uint32_t* cs[3] = {s_cs[0], s_cs[1], s_cs[2]};
         const uint2* pp[3] = {s_pos[0], s_pos[1], s_pos[2]};
-        step_particle<KN, FRAC, ANISO>(i, pi, vi, cell, cs, t.cs_lo, pp, t.p_lo, a);
+        step_particle<KN, FRAC, ANISO, false>(i, pi, vi, cell, cs, t.cs_lo, pp, t.p_lo, a);
     } else {
         if (!live) return;
         const uint32_t* cs[3] = {a.cell_start, a.cell_start, a.cell_start};
         const uint2* pp[3] = {a.pos_in, a.pos_in, a.pos_in};
         const uint32_t zero[3] = {0, 0, 0};
-        step_particle<KN, FRAC, ANISO>(i, pi, vi, cell, cs, zero, pp, zero, a);
+        step_particle<KN, FRAC, ANISO, true>(i, pi, vi, cell, cs, zero, pp, zero, a);
     }
 }
 
@@ -626,11 +747,26 @@ __global__ void gather_kernel(Source src, uint32_t p_lo, uint32_t p_hi, Grid g,
 // The few numbers the host needs after a binning: where the owned rows and their two boundary rows
 // start and end in the sorted arrays. out[0] = own_lo, [1] = end of the first owned row,
 // [2] = start of the last owned row, [3] = own_hi, [4] = total (with ghost rows), [5] = error flags,
-// [6] = tiles of step_kernel_c.
+// [6] = tiles of step_kernel_c, [7] = its tiles of the first owned row, [8] = its first tile of the last owned row.
+// The start of the upper ghost row is also published in the slab's HaloHeader for the lower neighbour's pushes.
+constexpr uint32_t kErrHaloTimeout = 8u;  // a step waited 20 s for a neighbour's halo
 __global__ void slab_counts_kernel(const uint32_t* __restrict__ cell_start, Grid g, const uint32_t* __restrict__ flags,
-                                   const uint32_t* __restrict__ couple_tiles, uint32_t* __restrict__ out) {
+                                   const uint32_t* __restrict__ couple_tiles, const uint32_t* __restrict__ tile_base,
+                                   HaloHeader* __restrict__ hdr, uint32_t* __restrict__ out) {
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
     out[6] = couple_tiles ? *couple_tiles : 0u;  // tiles of step_kernel_c (step_float.cuh)
+    out[7] = tile_base ? tile_base[1] : 0u;
+    out[8] = tile_base ? tile_base[g.own_rows - 1] : 0u;
+    if (hdr) {
+        hdr->own_hi = cell_start[(g.own_row0 + g.own_rows) * g.bx];
+        out[5] = flags[0] | (hdr->error ? kErrHaloTimeout : 0u);
+        out[0] = cell_start[g.own_row0 * g.bx];
+        out[1] = cell_start[(g.own_row0 + 1) * g.bx];
+        out[2] = cell_start[(g.own_row0 + g.own_rows - 1) * g.bx];
+        out[3] = hdr->own_hi;
+        out[4] = cell_start[g.cells];
+        return;
+    }
     out[0] = cell_start[g.own_row0 * g.bx];
     out[1] = cell_start[(g.own_row0 + 1) * g.bx];
     out[2] = cell_start[(g.own_row0 + g.own_rows - 1) * g.bx];
@@ -774,7 +910,9 @@ typedef struct ncclComm* ncclComm_t;
 typedef struct {
     char internal[128];
 } ncclUniqueId;
-constexpr int kNcclUint8 = 1;  // ncclDataType_t::ncclUint8
+constexpr int kNcclUint8 = 1;   // ncclDataType_t::ncclUint8
+constexpr int kNcclInt32 = 2;   // ncclDataType_t::ncclInt32
+constexpr int kNcclMin = 3;     // ncclRedOp_t::ncclMin
 
 struct NcclApi {
     void* lib = nullptr;
@@ -784,6 +922,7 @@ struct NcclApi {
     int (*CommAbort)(ncclComm_t) = nullptr;
     int (*Send)(const void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
     int (*Recv)(void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+    int (*AllReduce)(const void*, void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
     int (*GroupStart)() = nullptr;
     int (*GroupEnd)() = nullptr;
     const char* (*GetErrorString)(int) = nullptr;
@@ -856,8 +995,17 @@ struct PsimStepper {
     unsigned char* inbox[2] = {nullptr, nullptr};
     uint32_t* mig_counters = nullptr;  // 2
     uint32_t* mig_idx[2] = {nullptr, nullptr};
+    // halo push (HaloArgs): this slab's header, the neighbours' buffers and headers as this device sees them
+    HaloHeader* hdr = nullptr;
+    uint2* peer_pos[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};  // [side][buffer]
+    HaloHeader* peer_hdr[2] = {nullptr, nullptr};
+    void* ipc_mapped[2][3] = {{nullptr, nullptr, nullptr}, {nullptr, nullptr, nullptr}};  // to close at destroy
+    bool push = false;           // steps push their boundary rows (else: exchange after every step)
+    bool ghosts_by_push = false; // the ghost rows the next step reads are being written by the neighbours' last step
+    uint32_t halo_epoch = 0;     // epoch the last step published
+    uint32_t tiles_lo = 0, tile_hi0 = 0;  // couple tiles of the first owned row: [0, tiles_lo); of the last: [tile_hi0, ..)
     uint32_t* d_flags = nullptr;   // 1
-    uint32_t* d_counts = nullptr;  // 8
+    uint32_t* d_counts = nullptr;  // 16
     uint32_t* h_counts = nullptr;  // pinned, 16
 
     uint32_t n = 0;        // particles this stepper owns
@@ -1188,6 +1336,7 @@ bool load_nccl(PsimStepper* s) {
     api.CommAbort = reinterpret_cast<decltype(api.CommAbort)>(sym("ncclCommAbort"));
     api.Send = reinterpret_cast<decltype(api.Send)>(sym("ncclSend"));
     api.Recv = reinterpret_cast<decltype(api.Recv)>(sym("ncclRecv"));
+    api.AllReduce = reinterpret_cast<decltype(api.AllReduce)>(sym("ncclAllReduce"));
     api.GroupStart = reinterpret_cast<decltype(api.GroupStart)>(sym("ncclGroupStart"));
     api.GroupEnd = reinterpret_cast<decltype(api.GroupEnd)>(sym("ncclGroupEnd"));
     api.GetErrorString = reinterpret_cast<decltype(api.GetErrorString)>(sym("ncclGetErrorString"));
@@ -1347,10 +1496,11 @@ int bin_phase_scan(PsimStepper* s, bool need_counts) {
     int rc = enqueue_scan(s);
     if (rc) return rc;
     if (need_counts) {
-        slab_counts_kernel<<<1, 32, 0, s->stream>>>(s->cell_start, s->grid, s->d_flags, s->d_couple_tiles, s->d_counts);
+        slab_counts_kernel<<<1, 32, 0, s->stream>>>(s->cell_start, s->grid, s->d_flags, s->d_couple_tiles,
+                                                    s->float_grid ? s->tile_base : nullptr, s->hdr, s->d_counts);
         s->launches += 1;
         CK(cudaGetLastError());
-        CK(cudaMemcpyAsync(s->h_counts, s->d_counts, 8 * sizeof(uint32_t), cudaMemcpyDeviceToHost, s->stream));
+        CK(cudaMemcpyAsync(s->h_counts, s->d_counts, 16 * sizeof(uint32_t), cudaMemcpyDeviceToHost, s->stream));
     }
     return PSIM_OK;
 }
@@ -1363,6 +1513,8 @@ int bin_phase_commit(PsimStepper* s) {
     if (flags & kErrMigrantOverflow)
         return fail(s, PSIM_EMIGRATION, "slab %d: more than %u particles left for a neighbour slab in one re-bin "
                     "(PsimConfig.migrant_capacity)", s->rank, s->box_capacity);
+    if (flags & kErrHaloTimeout)
+        return fail(s, PSIM_ECUDA, "slab %d: a step waited 20 s for a neighbour's halo (did a neighbour rank die?)", s->rank);
     if (flags & (kErrMigrantTooFar | kErrMigrantOutside))
         return fail(s, PSIM_EMIGRATION, "slab %d: a particle moved past the adjacent slab between two re-bins", s->rank);
     uint32_t owned = h[3] - h[0];
@@ -1381,7 +1533,10 @@ int bin_phase_commit(PsimStepper* s) {
         if (h[6] > s->tiles_c_cap)
             return fail(s, PSIM_ECAPACITY, "internal: %u couple tiles, room for %u", h[6], s->tiles_c_cap);
         s->n_tiles_c = h[6];
+        s->tiles_lo = h[7];
+        s->tile_hi0 = h[8];
     }
+    s->ghosts_by_push = false;  // phase 4 of this binning delivers the ghost rows itself
     return PSIM_OK;
 }
 
@@ -1494,11 +1649,6 @@ int team_bin(const Team& t, bool ingest, const Particle* records, uint32_t count
 // ------------------------------------------------------------------------------------------------
 
 int enqueue_step(PsimStepper* s) {
-    if (s->n == 0) {
-        s->cur_pos ^= 1;  // ghost rows are exchanged into the buffer the next step reads
-        s->steps_executed += 1;
-        return PSIM_OK;
-    }
     StepArgs a;
     a.pos_in = s->pos[s->cur_pos];
     a.pos_out = s->pos[s->cur_pos ^ 1];
@@ -1510,6 +1660,41 @@ int enqueue_step(PsimStepper* s) {
     a.own_hi = s->own_hi;
     a.g = s->grid;
     a.ph = s->phys;
+    a.push = s->push ? 1u : 0u;
+    std::memset(&a.h, 0, sizeof a.h);
+    if (s->push) {
+        HaloArgs& h = a.h;
+        const int out = s->cur_pos ^ 1;
+        h.hdr = s->hdr;
+        for (int side = 0; side < 2; ++side) {
+            h.peer_out[side] = s->peer_pos[side][out];
+            h.peer_hdr[side] = s->peer_hdr[side];
+            h.wait_epoch[side] = s->ghosts_by_push ? s->halo_epoch : 0u;
+        }
+        h.lo_end = s->b_lo_end;
+        h.hi_start = s->b_hi_start;
+        if (s->float_path) {
+            h.lo_tiles = s->tiles_lo;
+            h.hi_tile0 = s->tile_hi0;
+        } else {
+            h.lo_tiles = div_up(s->b_lo_end - s->own_lo, kTile);
+            h.hi_tile0 = (s->b_hi_start - s->own_lo) / kTile;
+        }
+        s->halo_epoch += 1;
+        if (s->halo_epoch == 0) s->halo_epoch = 1;  // 0 means "nothing to wait for"
+        h.pub_epoch = s->halo_epoch;
+        s->ghosts_by_push = true;
+    }
+    if (s->n == 0) {  // nothing to step; the neighbours still get this step's epoch
+        if (s->push) {
+            halo_publish_kernel<<<1, 32, 0, s->stream>>>(a);
+            s->launches += 1;
+            CK(cudaGetLastError());
+        }
+        s->cur_pos ^= 1;  // ghost rows arrive in the buffer the next step reads
+        s->steps_executed += 1;
+        return PSIM_OK;
+    }
     uint32_t tiles = div_up(s->n, kTile);
     cudaEvent_t e0 = nullptr, e1 = nullptr;
     if (s->timing) {
@@ -1541,7 +1726,7 @@ int team_step(const Team& t) {
         if ((rc = enqueue_step(t.ranks[r]))) return rc;
         t.ranks[r]->fresh_scene = false;
     }
-    if (t.ranks[0]->nranks == 1) return PSIM_OK;
+    if (t.ranks[0]->nranks == 1 || t.ranks[0]->push) return PSIM_OK;  // pushed by the step kernel itself
     std::vector<XferOp> ops(t.count);
     for (int r = 0; r < t.count; ++r) ops[r] = ghost_positions_op(t.ranks[r]);
     return team_exchange(t, ops);
@@ -1705,6 +1890,10 @@ void psim_destroy(PsimStepper* s) {
     if (s->stream) cudaStreamSynchronize(s->stream);
     if (s->copy_stream) cudaStreamSynchronize(s->copy_stream);
     if (s->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(s->comm);
+    for (auto& side : s->ipc_mapped)
+        for (void*& m : side)
+            if (m) cudaIpcCloseMemHandle(m);
+    cudaFree(s->hdr);
     for (auto& ev : s->timing_events) {
         cudaEventDestroy(ev.first);
         cudaEventDestroy(ev.second);
@@ -1861,9 +2050,13 @@ int psim_create(const PsimConfig* config, PsimStepper** out) {
     CKC(cudaMalloc(&st->tiles, sizeof(TileDesc) * ((size_t)div_up((uint32_t)cap, kTile) + 1)));
     CKC(cudaMalloc(&st->staging, sizeof(Particle) * (size_t)st->ingest_cap));
     CKC(cudaMalloc(&st->snapshot, sizeof(Particle) * cap));
+    if (nranks > 1) {
+        CKC(cudaMalloc(&st->hdr, sizeof(HaloHeader)));
+        CKC(cudaMemset(st->hdr, 0, sizeof(HaloHeader)));
+    }
     CKC(cudaMalloc(&st->mig_counters, 2 * sizeof(uint32_t)));
     CKC(cudaMalloc(&st->d_flags, sizeof(uint32_t)));
-    CKC(cudaMalloc(&st->d_counts, 8 * sizeof(uint32_t)));
+    CKC(cudaMalloc(&st->d_counts, 16 * sizeof(uint32_t)));
     CKC(cudaMallocHost(&st->h_counts, 16 * sizeof(uint32_t)));
     CKC(cudaMemset(st->cell_start, 0, sizeof(uint32_t) * ((size_t)g.cells + 1 + kPadCells)));
     CKC(cudaMemset(st->d_flags, 0, sizeof(uint32_t)));
@@ -1892,6 +2085,83 @@ int psim_comm_unique_id(void* out128) {
     return PSIM_OK;
 }
 
+// What a slab hands its neighbours so that their step kernels can write its ghost rows: CUDA IPC handles of
+// its two position buffers and of its HaloHeader.
+struct HaloExport {
+    cudaIpcMemHandle_t pos[2];
+    cudaIpcMemHandle_t hdr;
+    uint32_t valid;
+    uint32_t _pad[3];
+};
+
+// Map the neighbours' buffers (one process per slab). Collective over the communicator. Any failure on any
+// rank leaves every rank on the send/recv halo exchange: the decision is an all-reduce.
+int connect_peers(PsimStepper* s) {
+    HaloExport mine;
+    std::memset(&mine, 0, sizeof mine);
+    const char* mode = getenv("PSIM_HALO");
+    int ok = !(mode && std::strcmp(mode, "nccl") == 0);
+    if (ok) {
+        ok = cudaIpcGetMemHandle(&mine.pos[0], s->pos[0]) == cudaSuccess &&
+             cudaIpcGetMemHandle(&mine.pos[1], s->pos[1]) == cudaSuccess &&
+             cudaIpcGetMemHandle(&mine.hdr, s->hdr) == cudaSuccess;
+        cudaGetLastError();
+    }
+    mine.valid = ok ? 1u : 0u;
+    HaloExport* d_io = nullptr;  // [0] mine, [1] from the lower, [2] from the upper neighbour
+    int* d_ok = nullptr;
+    CK(cudaMalloc(&d_io, 3 * sizeof(HaloExport)));
+    CK(cudaMalloc(&d_ok, sizeof(int)));
+    CK(cudaMemsetAsync(d_io, 0, 3 * sizeof(HaloExport), s->stream));
+    CK(cudaMemcpyAsync(d_io, &mine, sizeof mine, cudaMemcpyHostToDevice, s->stream));
+    XferOp op;
+    for (int side = 0; side < 2; ++side) {
+        if (side == 0 ? !(s->rank > 0) : !(s->rank + 1 < s->nranks)) continue;
+        op.send[side] = d_io;
+        op.recv[side] = d_io + 1 + side;
+        op.send_bytes[side] = op.recv_bytes[side] = sizeof(HaloExport);
+    }
+    int rc = exchange_nccl(s, op, s->stream);
+    if (rc) return rc;
+    HaloExport got[3];
+    CK(cudaMemcpyAsync(got, d_io, sizeof got, cudaMemcpyDeviceToHost, s->stream));
+    CK(cudaStreamSynchronize(s->stream));
+    for (int side = 0; side < 2 && ok; ++side) {
+        if (side == 0 ? !(s->rank > 0) : !(s->rank + 1 < s->nranks)) continue;
+        const HaloExport& e = got[1 + side];
+        if (!e.valid) {
+            ok = 0;
+            break;
+        }
+        const cudaIpcMemHandle_t* handles[3] = {&e.pos[0], &e.pos[1], &e.hdr};
+        for (int k = 0; k < 3 && ok; ++k) {
+            void* p = nullptr;
+            if (cudaIpcOpenMemHandle(&p, *handles[k], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+                cudaGetLastError();
+                ok = 0;
+            } else {
+                s->ipc_mapped[side][k] = p;
+            }
+        }
+    }
+    // everybody pushes or nobody does
+    CK(cudaMemcpyAsync(d_ok, &ok, sizeof ok, cudaMemcpyHostToDevice, s->stream));
+    CKN(g_nccl.AllReduce(d_ok, d_ok, 1, kNcclInt32, kNcclMin, s->comm, s->stream));
+    CK(cudaMemcpyAsync(&ok, d_ok, sizeof ok, cudaMemcpyDeviceToHost, s->stream));
+    CK(cudaStreamSynchronize(s->stream));
+    cudaFree(d_io);
+    cudaFree(d_ok);
+    s->push = ok != 0;
+    if (s->push) {
+        for (int side = 0; side < 2; ++side) {
+            s->peer_pos[side][0] = static_cast<uint2*>(s->ipc_mapped[side][0]);
+            s->peer_pos[side][1] = static_cast<uint2*>(s->ipc_mapped[side][1]);
+            s->peer_hdr[side] = static_cast<HaloHeader*>(s->ipc_mapped[side][2]);
+        }
+    }
+    return PSIM_OK;
+}
+
 int psim_comm_init(PsimStepper* s, const void* unique_id128) {
     if (!s || !unique_id128) return PSIM_EINVAL;
     int rc = check_lone(s, "psim_comm_init");
@@ -1903,8 +2173,10 @@ int psim_comm_init(PsimStepper* s, const void* unique_id128) {
     ncclUniqueId id;
     std::memcpy(&id, unique_id128, sizeof id);
     CKN(g_nccl.CommInitRank(&s->comm, s->nranks, id, s->rank));
-    return PSIM_OK;
+    return connect_peers(s);
 }
+
+int psim_halo_mode(const PsimStepper* s) { return s ? (s->nranks == 1 ? 0 : (s->push ? 2 : 1)) : 0; }
 
 int psim_upload_frame(PsimStepper* s, const FrameHeader* frame) {
     if (!s || !frame) return PSIM_EINVAL;
@@ -2129,10 +2401,21 @@ int psim_group_create(PsimStepper* const* steppers, uint32_t count, PsimGroup** 
     PsimGroup* g = new PsimGroup;
     g->ranks.assign(steppers, steppers + count);
     g->stream = steppers[0]->own_stream;
-    for (PsimStepper* m : g->ranks) {
+    const char* mode = getenv("PSIM_HALO");
+    const bool push = !(mode && std::strcmp(mode, "nccl") == 0);
+    for (uint32_t r = 0; r < count; ++r) {
+        PsimStepper* m = g->ranks[r];
         cudaStreamSynchronize(m->stream);
         m->group = g;
         m->stream = g->stream;
+        m->push = push && count > 1;  // same device: the neighbours' buffers are plain pointers
+        for (int side = 0; side < 2; ++side) {
+            const int peer = side == 0 ? (int)r - 1 : (int)r + 1;
+            const bool has = m->push && peer >= 0 && peer < (int)count;
+            m->peer_pos[side][0] = has ? g->ranks[peer]->pos[0] : nullptr;
+            m->peer_pos[side][1] = has ? g->ranks[peer]->pos[1] : nullptr;
+            m->peer_hdr[side] = has ? g->ranks[peer]->hdr : nullptr;
+        }
     }
     *out = g;
     return PSIM_OK;
@@ -2144,6 +2427,11 @@ void psim_group_destroy(PsimGroup* g) {
         cudaStreamSynchronize(g->stream);
         m->group = nullptr;
         m->stream = m->own_stream;
+        m->push = false;
+        for (int side = 0; side < 2; ++side) {
+            m->peer_pos[side][0] = m->peer_pos[side][1] = nullptr;
+            m->peer_hdr[side] = nullptr;
+        }
     }
     delete g;
 }

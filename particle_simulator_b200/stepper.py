@@ -117,6 +117,8 @@ def lib() -> ctypes.CDLL:
         L.psim_group_last_error.argtypes = [vp]
         L.psim_group_particle_count.restype = ctypes.c_uint32
         L.psim_group_particle_count.argtypes = [vp]
+        L.psim_halo_mode.restype = ctypes.c_int
+        L.psim_halo_mode.argtypes = [vp]
         L.psim_particle_count.restype = ctypes.c_uint32
         L.psim_cell_count.restype = ctypes.c_uint32
         for name in ("psim_steps_executed", "psim_rebins_executed", "psim_kernel_launches"):
@@ -229,6 +231,11 @@ class Stepper:
     def comm_init(self, unique_id: bytes) -> None:
         assert len(unique_id) == 128
         self._check(lib().psim_comm_init(self._h, ctypes.c_char_p(unique_id)))
+
+    @property
+    def halo_mode(self) -> int:
+        """0: single slab, 1: send/recv after every step, 2: pushed by the step kernel over peer memory."""
+        return int(lib().psim_halo_mode(self._h))
 
     def slab_info(self) -> dict:
         info = CSlabInfo()

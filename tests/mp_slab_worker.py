@@ -30,6 +30,11 @@ def main() -> int:
     st = Stepper(wl.grid_log2, int(0.75 * n) if world > 1 else n, device=local, slab_rank=rank, slab_count=world,
                  ingest_capacity=n)
     st.comm_init(uid)
+    want_mode = {"push": 2, "nccl": 1}.get(os.environ.get("PSIM_EXPECT_HALO", ""), 0)
+    if rank == 0:
+        print(f"halo mode {st.halo_mode} (1: send/recv after every step, 2: pushed by the step kernel)", flush=True)
+    if want_mode and world > 1 and st.halo_mode != want_mode:
+        raise RuntimeError(f"rank {rank}: halo mode {st.halo_mode}, expected {want_mode}")
     single = Stepper(wl.grid_log2, n, device=local) if rank == 0 else None
     st.upload(wl.frame)  # the whole scene: the slab keeps its own rows
     if single:

@@ -17,15 +17,21 @@ def _gpus() -> int:
     return torch.cuda.device_count()
 
 
+@pytest.mark.parametrize("halo", ["push", "nccl"])
 @pytest.mark.parametrize("world", [2, 4, 8])
-def test_nccl_slabs_are_bit_identical_to_single_slab(world):
+def test_nccl_slabs_are_bit_identical_to_single_slab(world, halo):
+    """halo = push: the step kernel stores boundary rows into the neighbours' ghost rows over peer memory (CUDA IPC);
+    halo = nccl: an ncclSend/ncclRecv pair per neighbour after every step (PSIM_HALO=nccl)."""
     if _gpus() < world:
         pytest.skip(f"needs {world} GPUs, this box has {_gpus()}")
+    env = dict(os.environ, PSIM_EXPECT_HALO=halo)
+    if halo == "nccl":
+        env["PSIM_HALO"] = "nccl"
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}",
-           "--master-addr", "127.0.0.1", "--master-port", str(29600 + world),
+           "--master-addr", "127.0.0.1", "--master-port", str(29600 + world + (10 if halo == "nccl" else 0)),
            os.path.join(REPO, "tests", "mp_slab_worker.py"), "3"]
     # own session: if a rank hangs, the whole process group is killed, never left spinning on the GPUs
-    proc = subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, cwd=REPO,
+    proc = subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, cwd=REPO, env=env,
                             start_new_session=True)
     try:
         out, err = proc.communicate(timeout=240)

@@ -109,6 +109,40 @@ def test_liquid_1m_in_8_slabs():
     assert n == 2
 
 
+def test_group_with_copies_after_every_step_matches_too(golden, monkeypatch):
+    """PSIM_HALO=nccl switches the in-process group from pushes by the step kernel to a device-to-device copy of
+    the boundary rows after every step (the shape of the send/recv exchange)."""
+    from particle_simulator_b200.stepper import SlabGroup
+
+    g = golden("gas10k")
+    meta = g["meta"][0].copy()
+    meta["steps_per_frame"] = 35
+    fb = frame_from(g["input"], meta)
+    with SlabGroup((6, 6), 4, fb.count, ingest_capacity=fb.count) as gr:
+        assert [s.halo_mode for s in gr.slabs] == [2] * 4
+    monkeypatch.setenv("PSIM_HALO", "nccl")
+    n = 0
+    for single, group, gr in run_both(fb, (6, 6), 4, frames=2):
+        assert [s.halo_mode for s in gr.slabs] == [1] * 4
+        assert single.tobytes() == group.tobytes()
+        n += 1
+    assert n == 2
+
+
+def test_fine_grid_slabs_run_the_couples_kernel():
+    """1024 x 1024 cells: the slabs run step_kernel_c; its tiles of the first / last owned row push the halo."""
+    from particle_simulator_b200.workloads import lattice
+
+    w = lattice(300, 300, (10, 10), 1.04, 100.0, 200.0, seed=5)
+    w.frame.metadata["steps_per_frame"] = 35
+    n = 0
+    for single, group, gr in run_both(w.frame, w.grid_log2, 4, frames=2):
+        assert single.tobytes() == group.tobytes()
+        assert all(s.tile_stats()["float_path"] == 1 for s in gr.slabs)
+        n += 1
+    assert n == 2
+
+
 def test_native_schedule_matches_too(golden):
     from particle_simulator_b200.stepper import SCHEDULE_NATIVE, SlabGroup, Stepper
 
