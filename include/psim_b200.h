@@ -55,6 +55,10 @@ typedef struct PsimConfig {
     uint32_t migrant_capacity; /* particles that can move to ONE neighbour slab in one re-bin; 0 => same   */
     uint32_t ingest_capacity;  /* records an uploaded frame can hold (a slab is usually handed the whole
                                   scene and keeps its own rows); 0 => max_particles                        */
+    uint32_t snapshot_buffers; /* 0 or 1: one snapshot buffer; 2: two that alternate, so that the snapshot of the
+                                  previous frame can be downloaded (psim_download_frame_ex, age 1) while the next
+                                  frame, its snapshot included, is already enqueued -- the double buffering of the
+                                  reference's main loop (cuda_simulator.cu:28-37)                           */
 } PsimConfig;
 
 /* Defaults: 64x64 cells (the reference grid), 65536 particles, reference schedule, device -1. */
@@ -105,6 +109,14 @@ int psim_sync(PsimStepper* s);
  * reference's compacted slot array has). dst->particle_count must hold dst's capacity on entry.
  * Waits only for the snapshot, not for frames enqueued after it. */
 int psim_download_frame(PsimStepper* s, FrameHeader* dst);
+/* The snapshot packed `age` snapshots ago: 0 = the latest (= psim_download_frame), 1 = the one before it
+ * (needs PsimConfig.snapshot_buffers = 2). */
+int psim_download_frame_ex(PsimStepper* s, uint32_t age, FrameHeader* dst);
+
+/* Page-locked host memory for frames (uploads and downloads from pageable memory are staged by the driver
+ * and run at a fraction of the link rate). NULL on failure. */
+void* psim_host_alloc(size_t bytes);
+void psim_host_free(void* p);
 
 /* Introspection for parity checks and benchmarks. */
 uint32_t psim_particle_count(const PsimStepper* s);          /* live particles on the device      */

@@ -19,6 +19,7 @@ CSRC = os.path.join(PKG_DIR, "csrc")
 INCLUDE = os.path.join(REPO, "include")
 LIB_IO = os.path.join(PKG_DIR, "libparticle_io_c.so")
 LIB_PSIM = os.path.join(PKG_DIR, "libpsim_b200.so")
+SIMULATOR = os.path.join(PKG_DIR, "psim_simulator")
 
 NVCC_ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 
@@ -65,12 +66,24 @@ def build_psim(force: bool = False, verbose: bool = False) -> str:
     return LIB_PSIM
 
 
+def build_simulator(force: bool = False) -> str:
+    """The simulator process (drop-in for the reference's cuda_simulator binary): plain C++ over the two C ABIs."""
+    src = [os.path.join(CSRC, "simulator_main.cpp")]
+    deps = src + [os.path.join(INCLUDE, "psim_b200.h"), os.path.join(INCLUDE, "particle_io.h"), LIB_IO, LIB_PSIM]
+    if force or _stale(SIMULATOR, deps):
+        _run(["g++", "-O2", "-std=c++17", "-Wall", "-I" + INCLUDE, *src, "-o", SIMULATOR, "-L" + PKG_DIR,
+              "-lpsim_b200", "-lparticle_io_c", "-Wl,-rpath,$ORIGIN", "-lpthread"])
+    return SIMULATOR
+
+
 def build_all(force: bool = False) -> None:
     build_io(force)
     build_psim(force)
+    build_simulator(force)
 
 
 if __name__ == "__main__":
     build_all(force="--force" in sys.argv)
     print(LIB_IO)
     print(LIB_PSIM)
+    print(SIMULATOR)

@@ -192,12 +192,20 @@ __global__ void __launch_bounds__(kCouples, 9) step_kernel_c(const StepArgs a, c
         const float to_odd = (zq & 1u) ? -pf.zone_shift : pf.zone_shift;
         const uint2* __restrict__ src = a.pos_in + r0;
         float4* out = s_nb + dst;
-#pragma unroll 1
-        for (uint32_t k = 0; k < r1 - r0; ++k) {
-            const uint2 p = __ldcg(src + k);  // L2: a ghost row is written by the neighbour while this kernel runs
-            const float xe = __int2float_rn((int)(p.x - xo0)) * pf.sx;
-            const float y = __int2float_rn((int)(p.y - t.yc)) * pf.sy;
-            out[k] = make_float4(xe, y, xe + to_odd, y);
+        const uint32_t n = r1 - r0;
+        for (uint32_t base = 0; base < n; base += 4) {  // four loads in flight: a cell holds 4-6 particles
+            uint2 p[4];
+#pragma unroll
+            for (uint32_t u = 0; u < 4; ++u)
+                if (base + u < n) p[u] = __ldcg(src + base + u);  // L2: a ghost row is written by the neighbour meanwhile
+#pragma unroll
+            for (uint32_t u = 0; u < 4; ++u) {
+                if (base + u < n) {
+                    const float xe = __int2float_rn((int)(p[u].x - xo0)) * pf.sx;
+                    const float y = __int2float_rn((int)(p[u].y - t.yc)) * pf.sy;
+                    out[base + u] = make_float4(xe, y, xe + to_odd, y);
+                }
+            }
         }
     }
     __syncthreads();

@@ -956,8 +956,12 @@ struct PsimStepper {
     cudaStream_t own_stream = nullptr;
     cudaStream_t stream = nullptr;       // where the step loop runs (own_stream, the caller's, or the group's)
     cudaStream_t copy_stream = nullptr;  // snapshot download
-    cudaEvent_t snapshot_ready = nullptr;
-    cudaEvent_t snapshot_consumed = nullptr;
+    // Snapshots: one buffer, or two that alternate (PsimConfig.snapshot_buffers = 2) so that the previous
+    // frame's snapshot can be copied out while the next frame, pack included, is already enqueued.
+    int nsnap = 1, snap_latest = 0;
+    uint64_t snaps_taken = 0;
+    cudaEvent_t snapshot_ready[2] = {nullptr, nullptr};
+    cudaEvent_t snapshot_consumed[2] = {nullptr, nullptr};
 
     // capacities
     uint32_t ghost_cap = 0;     // particles per ghost row
@@ -989,7 +993,7 @@ struct PsimStepper {
     uint32_t* rank_in_cell = nullptr;
     uint32_t* perm = nullptr;
     Particle* staging = nullptr;   // ingest buffer (wire-format records)
-    Particle* snapshot = nullptr;  // packed snapshot of the owned particles (wire-format records)
+    Particle* snapshot[2] = {nullptr, nullptr};  // packed snapshots of the owned particles (wire-format records)
     uint32_t ingest_cap = 0;       // records the ingest buffer holds
     unsigned char* outbox[2] = {nullptr, nullptr};
     unsigned char* inbox[2] = {nullptr, nullptr};
@@ -1014,8 +1018,8 @@ struct PsimStepper {
     Source src{};          // candidates of the binning in flight
     bool binning_is_ingest = false;
 
-    uint32_t snapshot_n = 0;
-    FrameMetadata snapshot_meta{};
+    uint32_t snapshot_n[2] = {0, 0};
+    FrameMetadata snapshot_meta[2]{};
     bool has_scene = false;
     bool has_snapshot = false;
     bool fresh_scene = false;  // nothing has been stepped since the ingest: the binning is current
@@ -1733,17 +1737,20 @@ int team_step(const Team& t) {
 }
 
 int enqueue_snapshot(PsimStepper* s) {
-    // the previous snapshot must have left the staging buffer before it is overwritten
-    CK(cudaStreamWaitEvent(s->stream, s->snapshot_consumed, 0));
+    const int k = s->snaps_taken ? (s->snap_latest + 1) % s->nsnap : 0;
+    // the snapshot that lived in this buffer must have left it before it is overwritten
+    CK(cudaStreamWaitEvent(s->stream, s->snapshot_consumed[k], 0));
     if (s->n) {
         pack_kernel<<<div_up(s->n, 256), 256, 0, s->stream>>>(s->pos[s->cur_pos], s->vel[s->cur_vel], s->ty[s->cur_ty],
-                                                              s->own_lo, s->own_hi, s->snapshot);
+                                                              s->own_lo, s->own_hi, s->snapshot[k]);
         s->launches += 1;
         CK(cudaGetLastError());
     }
-    CK(cudaEventRecord(s->snapshot_ready, s->stream));
-    s->snapshot_n = s->n;
-    s->snapshot_meta = s->meta;
+    CK(cudaEventRecord(s->snapshot_ready[k], s->stream));
+    s->snapshot_n[k] = s->n;
+    s->snapshot_meta[k] = s->meta;
+    s->snap_latest = k;
+    s->snaps_taken += 1;
     s->has_snapshot = true;
     return PSIM_OK;
 }
@@ -1847,13 +1854,19 @@ void write_header(FrameHeader* dst, const FrameMetadata& meta, uint32_t count) {
     dst->particle_count = count;
 }
 
-// Copy this slab's packed snapshot to `out` (host); waits only for the snapshot.
-int download_records(PsimStepper* s, Particle* out) {
-    CK(cudaStreamWaitEvent(s->copy_stream, s->snapshot_ready, 0));
-    if (s->snapshot_n)
-        CK(cudaMemcpyAsync(out, s->snapshot, sizeof(Particle) * (size_t)s->snapshot_n, cudaMemcpyDeviceToHost,
+// Which buffer holds the snapshot taken `age` snapshots ago (0: the latest), or -1.
+int snapshot_index(const PsimStepper* s, uint32_t age) {
+    if (!s->has_snapshot || age >= (uint32_t)s->nsnap || age >= s->snaps_taken) return -1;
+    return (s->snap_latest - (int)age + s->nsnap) % s->nsnap;
+}
+
+// Copy one of this slab's packed snapshots to `out` (host); waits only for that snapshot.
+int download_records(PsimStepper* s, int k, Particle* out) {
+    CK(cudaStreamWaitEvent(s->copy_stream, s->snapshot_ready[k], 0));
+    if (s->snapshot_n[k])
+        CK(cudaMemcpyAsync(out, s->snapshot[k], sizeof(Particle) * (size_t)s->snapshot_n[k], cudaMemcpyDeviceToHost,
                            s->copy_stream));
-    CK(cudaEventRecord(s->snapshot_consumed, s->copy_stream));
+    CK(cudaEventRecord(s->snapshot_consumed[k], s->copy_stream));
     CK(cudaStreamSynchronize(s->copy_stream));
     return PSIM_OK;
 }
@@ -1920,13 +1933,16 @@ void psim_destroy(PsimStepper* s) {
     cudaFree(s->cell_id);
     cudaFree(s->tiles);
     cudaFree(s->staging);
-    cudaFree(s->snapshot);
+    cudaFree(s->snapshot[0]);
+    cudaFree(s->snapshot[1]);
     cudaFree(s->mig_counters);
     cudaFree(s->d_flags);
     cudaFree(s->d_counts);
     if (s->h_counts) cudaFreeHost(s->h_counts);
-    if (s->snapshot_ready) cudaEventDestroy(s->snapshot_ready);
-    if (s->snapshot_consumed) cudaEventDestroy(s->snapshot_consumed);
+    for (int k = 0; k < 2; ++k) {
+        if (s->snapshot_ready[k]) cudaEventDestroy(s->snapshot_ready[k]);
+        if (s->snapshot_consumed[k]) cudaEventDestroy(s->snapshot_consumed[k]);
+    }
     if (s->own_stream) cudaStreamDestroy(s->own_stream);
     if (s->copy_stream) cudaStreamDestroy(s->copy_stream);
     delete s;
@@ -2014,8 +2030,11 @@ int psim_create(const PsimConfig* config, PsimStepper** out) {
     CKC(cudaStreamCreateWithFlags(&st->own_stream, cudaStreamNonBlocking));
     CKC(cudaStreamCreateWithFlags(&st->copy_stream, cudaStreamNonBlocking));
     st->stream = st->own_stream;
-    CKC(cudaEventCreateWithFlags(&st->snapshot_ready, cudaEventDisableTiming));
-    CKC(cudaEventCreateWithFlags(&st->snapshot_consumed, cudaEventDisableTiming));
+    st->nsnap = config->snapshot_buffers >= 2 ? 2 : 1;
+    for (int k = 0; k < st->nsnap; ++k) {
+        CKC(cudaEventCreateWithFlags(&st->snapshot_ready[k], cudaEventDisableTiming));
+        CKC(cudaEventCreateWithFlags(&st->snapshot_consumed[k], cudaEventDisableTiming));
+    }
     for (int k = 0; k < 2; ++k) {
         CKC(cudaMalloc(&st->pos[k], sizeof(uint2) * (cap_total + kPadParticles)));
         CKC(cudaMemset(st->pos[k], 0, sizeof(uint2) * (cap_total + kPadParticles)));
@@ -2049,7 +2068,7 @@ int psim_create(const PsimConfig* config, PsimStepper** out) {
     CKC(cudaMalloc(&st->cell_id, sizeof(uint32_t) * cap_total));
     CKC(cudaMalloc(&st->tiles, sizeof(TileDesc) * ((size_t)div_up((uint32_t)cap, kTile) + 1)));
     CKC(cudaMalloc(&st->staging, sizeof(Particle) * (size_t)st->ingest_cap));
-    CKC(cudaMalloc(&st->snapshot, sizeof(Particle) * cap));
+    for (int k = 0; k < st->nsnap; ++k) CKC(cudaMalloc(&st->snapshot[k], sizeof(Particle) * cap));
     if (nranks > 1) {
         CKC(cudaMalloc(&st->hdr, sizeof(HaloHeader)));
         CKC(cudaMemset(st->hdr, 0, sizeof(HaloHeader)));
@@ -2272,17 +2291,35 @@ int psim_sync(PsimStepper* s) {
     return PSIM_OK;
 }
 
-int psim_download_frame(PsimStepper* s, FrameHeader* dst) {
+int psim_download_frame_ex(PsimStepper* s, uint32_t age, FrameHeader* dst) {
     if (!s || !dst) return PSIM_EINVAL;
-    if (!s->has_snapshot) return fail(s, PSIM_ESTATE, "psim_download_frame: no snapshot has been packed");
+    const int k = snapshot_index(s, age);
+    if (k < 0)
+        return fail(s, PSIM_ESTATE, "psim_download_frame: no snapshot of age %u (%llu packed so far, %d buffer%s)", age,
+                    (unsigned long long)s->snaps_taken, s->nsnap, s->nsnap > 1 ? "s" : "");
     CK(cudaSetDevice(s->device));
-    if (dst->particle_count < s->snapshot_n)
+    if (dst->particle_count < s->snapshot_n[k])
         return fail(s, PSIM_ECAPACITY, "psim_download_frame: destination holds %u particles, snapshot has %u",
-                    dst->particle_count, s->snapshot_n);
-    int rc = download_records(s, dst->particles);
+                    dst->particle_count, s->snapshot_n[k]);
+    int rc = download_records(s, k, dst->particles);
     if (rc) return rc;
-    write_header(dst, s->snapshot_meta, s->snapshot_n);
+    write_header(dst, s->snapshot_meta[k], s->snapshot_n[k]);
     return PSIM_OK;
+}
+
+int psim_download_frame(PsimStepper* s, FrameHeader* dst) { return psim_download_frame_ex(s, 0, dst); }
+
+void* psim_host_alloc(size_t bytes) {
+    void* p = nullptr;
+    if (cudaMallocHost(&p, bytes ? bytes : 1) != cudaSuccess) {
+        cudaGetLastError();
+        return nullptr;
+    }
+    return p;
+}
+
+void psim_host_free(void* p) {
+    if (p) cudaFreeHost(p);
 }
 
 uint32_t psim_particle_count(const PsimStepper* s) { return s ? s->n : 0; }
@@ -2547,8 +2584,9 @@ int psim_group_download_frame(PsimGroup* g, FrameHeader* dst) {
     PsimStepper* s = g->ranks[0];
     uint64_t total = 0;
     for (PsimStepper* m : g->ranks) {
-        if (!m->has_snapshot) return group_fail(g, fail(s, PSIM_ESTATE, "psim_group_download_frame: no snapshot has been packed"));
-        total += m->snapshot_n;
+        const int k = snapshot_index(m, 0);
+        if (k < 0) return group_fail(g, fail(s, PSIM_ESTATE, "psim_group_download_frame: no snapshot has been packed"));
+        total += m->snapshot_n[k];
     }
     if (dst->particle_count < total)
         return group_fail(g, fail(s, PSIM_ECAPACITY, "psim_group_download_frame: destination holds %u particles, "
@@ -2557,11 +2595,12 @@ int psim_group_download_frame(PsimGroup* g, FrameHeader* dst) {
     // slabs in rank order = ascending cell rows = the cell-major order of a single-slab snapshot
     Particle* out = dst->particles;
     for (PsimStepper* m : g->ranks) {
-        int rc = download_records(m, out);
+        const int k = snapshot_index(m, 0);
+        int rc = download_records(m, k, out);
         if (rc) return group_fail(g, rc);
-        out += m->snapshot_n;
+        out += m->snapshot_n[k];
     }
-    write_header(dst, s->snapshot_meta, (uint32_t)total);
+    write_header(dst, s->snapshot_meta[snapshot_index(s, 0)], (uint32_t)total);
     return PSIM_OK;
 }
 

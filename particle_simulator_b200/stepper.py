@@ -46,6 +46,7 @@ class CConfig(ctypes.Structure):
         ("ghost_capacity", ctypes.c_uint32),
         ("migrant_capacity", ctypes.c_uint32),
         ("ingest_capacity", ctypes.c_uint32),
+        ("snapshot_buffers", ctypes.c_uint32),
     ]
 
 
@@ -91,6 +92,7 @@ def lib() -> ctypes.CDLL:
             "psim_snapshot_async": [vp],
             "psim_sync": [vp],
             "psim_download_frame": [vp, vp],
+            "psim_download_frame_ex": [vp, ctypes.c_uint32, vp],
             "psim_get_cell_start": [vp, vp],
             "psim_enable_step_timing": [vp, ctypes.c_int],
             "psim_get_step_timing": [vp, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_uint64)],
@@ -134,7 +136,7 @@ class Stepper:
     def __init__(self, grid_log2: tuple[int, int] = (6, 6), max_particles: int = 65536,
                  schedule: int = SCHEDULE_REFERENCE, rebin_every: int = 0, device: int = -1,
                  use_graph: bool = False, slab_rank: int = 0, slab_count: int = 1, ghost_capacity: int = 0,
-                 migrant_capacity: int = 0, ingest_capacity: int = 0):
+                 migrant_capacity: int = 0, ingest_capacity: int = 0, snapshot_buffers: int = 1):
         L = lib()
         cfg = L.psim_default_config()
         cfg.grid_x_log2, cfg.grid_y_log2 = grid_log2
@@ -145,6 +147,7 @@ class Stepper:
         cfg.use_graph = 1 if use_graph else 0
         cfg.slab_rank, cfg.slab_count = slab_rank, slab_count
         cfg.ghost_capacity, cfg.migrant_capacity, cfg.ingest_capacity = ghost_capacity, migrant_capacity, ingest_capacity
+        cfg.snapshot_buffers = snapshot_buffers
         self._h = ctypes.c_void_p()
         rc = L.psim_create(ctypes.byref(cfg), ctypes.byref(self._h))
         if rc != 0:
@@ -211,11 +214,12 @@ class Stepper:
     def sync(self) -> None:
         self._check(lib().psim_sync(self._h))
 
-    def download(self, frame: FrameBuffer | None = None) -> FrameBuffer:
+    def download(self, frame: FrameBuffer | None = None, age: int = 0) -> FrameBuffer:
+        """The snapshot packed `age` snapshots ago (0: the latest; 1 needs snapshot_buffers=2)."""
         if frame is None:
             frame = FrameBuffer(max(self.particle_count, 1))
         frame.count = frame.capacity
-        self._check(lib().psim_download_frame(self._h, frame.ptr))
+        self._check(lib().psim_download_frame_ex(self._h, age, frame.ptr))
         return frame
 
     # -- slab decomposition, one process per slab (NCCL) -------------------------------------

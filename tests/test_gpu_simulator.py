@@ -1,0 +1,166 @@
+"""The simulator process (particle_simulator_b200/psim_simulator, csrc/simulator_main.cpp) against a fake editor.
+
+The reference's simulator is a TCP client of the editor (cuda_simulator/src/lib/frontend.hpp:22-25,
+particle_editor/src/backend.rs:37): it waits for a scene, echoes the ingested scene, then streams one compacted
+snapshot per frame; a header-only frame updates the metadata, a frame with particles replaces the scene
+(cuda_simulator/src/cuda_simulator.cu:7-54). The same conversation is held here over a loopback socket and over
+the file transport (frontend.hpp:16-20), and every frame received is compared with the in-process stepper.
+"""
+import os
+import socket
+import subprocess
+import time
+
+import numpy as np
+import pytest
+
+from conftest import frame_from
+from particle_simulator_b200 import FrameBuffer, _build, io
+from particle_simulator_b200.frame import HEADER_DTYPE, packet_size
+
+pytestmark = pytest.mark.gpu
+
+
+def recv_exact(conn: socket.socket, n: int) -> bytes:
+    chunks = []
+    while n:
+        b = conn.recv(min(n, 1 << 20))
+        if not b:
+            raise ConnectionError("the simulator closed the connection")
+        chunks.append(b)
+        n -= len(b)
+    return b"".join(chunks)
+
+
+def recv_frame(conn: socket.socket) -> FrameBuffer:
+    head = recv_exact(conn, HEADER_DTYPE.itemsize)
+    count = int(np.frombuffer(head, dtype=HEADER_DTYPE)[0]["particle_count"])
+    return FrameBuffer.from_bytes(head + recv_exact(conn, packet_size(count) - len(head)))
+
+
+def reference_frames(fb: FrameBuffer, grid, frames: int) -> list[bytes]:
+    """[ingested scene, frame 1, frame 2, ...] from the stepper in this process."""
+    from particle_simulator_b200.stepper import Stepper
+
+    out = []
+    with Stepper(grid, max(fb.count, 65536)) as st:
+        st.upload(fb)
+        out.append(st.download().tobytes())
+        for _ in range(frames):
+            st.run_frame_async()
+            st.sync()
+            out.append(st.download().tobytes())
+    return out
+
+
+@pytest.fixture()
+def simulator():
+    _build.build_all()
+    procs = []
+
+    def start(*args):
+        p = subprocess.Popen([_build.SIMULATOR, *args], stderr=subprocess.PIPE, text=True)
+        procs.append(p)
+        return p
+
+    yield start
+    for p in procs:
+        if p.poll() is None:
+            p.kill()
+        p.wait()
+
+
+def test_tcp_conversation_with_a_fake_editor(golden, simulator):
+    g = golden("hex2500")
+    meta = g["meta"][0].copy()
+    meta["steps_per_frame"] = 18
+    scene = frame_from(g["input"], meta)
+    want = reference_frames(scene, (6, 6), 3)
+
+    srv = socket.socket()
+    srv.bind(("127.0.0.1", 0))
+    srv.listen(1)
+    srv.settimeout(60)
+    proc = simulator("--connect", f"127.0.0.1:{srv.getsockname()[1]}", "--verbose")
+    conn, _ = srv.accept()
+    conn.settimeout(60)
+    try:
+        time.sleep(0.05)  # the simulator polls for its first scene
+        conn.sendall(scene.tobytes())
+        echo = recv_frame(conn)
+        assert echo.tobytes() == want[0]                                  # the ingested scene, binned order
+        assert echo.particles.tobytes() == g["binned"].tobytes()          # = the reference's own binning
+        for k in (1, 2, 3):
+            assert recv_frame(conn).tobytes() == want[k], f"frame {k}"   # bit-identical to the in-process stepper
+
+        # interactive mode: a header-only frame changes the metadata a frame or two later, the particles live on
+        upd = FrameBuffer(1, meta)
+        upd.metadata["steps_per_frame"] = 5
+        conn.sendall(upd.tobytes())
+        seen = None
+        for _ in range(12):
+            f = recv_frame(conn)
+            assert f.count == scene.count
+            if int(f.metadata["steps_per_frame"]) == 5:
+                seen = f
+                break
+        assert seen is not None, "the metadata update never showed up in a snapshot"
+
+        # a new scene on another box: 128 x 128 cells, more particles; echoed in binned order, then stepped
+        big = FrameBuffer(120 * 120)
+        big.metadata["box_width"] = 100e-9
+        big.metadata["box_height"] = 100e-9
+        big.metadata["steps_per_frame"] = 18
+        io.scene_hex_square(big, 120, 120, (50e-9, 50e-9), 1.0, 5.0, 5.0, 1, seed=9)
+        want_big = reference_frames(big, (7, 7), 2)
+        conn.sendall(big.tobytes())
+        while True:
+            f = recv_frame(conn)
+            if f.count == big.count:
+                break
+            assert f.count == scene.count  # frames of the old scene still in flight
+        assert f.tobytes() == want_big[0]
+        assert recv_frame(conn).tobytes() == want_big[1]
+        assert recv_frame(conn).tobytes() == want_big[2]
+    finally:
+        conn.close()
+        srv.close()
+    assert proc.wait(timeout=30) == 0, proc.stderr.read()[-2000:]
+
+
+def test_file_transport(golden, simulator, tmp_path):
+    g = golden("liquid4k")
+    meta = g["meta"][0].copy()
+    meta["steps_per_frame"] = 35
+    scene = frame_from(g["input"], meta)
+    want = reference_frames(scene, (6, 6), 2)
+    fin, fout = tmp_path / "backend_in.bin", tmp_path / "backend_out.bin"
+    fin.write_bytes(scene.tobytes())
+    fout.write_bytes(b"")  # the writer appends and does not create (particle_io/src/writer.rs:17)
+    proc = simulator("--files", str(fin), str(fout), "--frames", "2")
+    assert proc.wait(timeout=60) == 0, proc.stderr.read()[-2000:]
+    assert fout.read_bytes() == b"".join(want)
+
+
+def test_previous_snapshot_can_be_downloaded_while_the_next_frame_is_enqueued(golden):
+    """PsimConfig.snapshot_buffers = 2: the double buffering of the reference's main loop (cuda_simulator.cu:28-37)."""
+    from particle_simulator_b200.stepper import PsimError, Stepper
+
+    g = golden("hex2500")
+    meta = g["meta"][0].copy()
+    meta["steps_per_frame"] = 18
+    fb = frame_from(g["input"], meta)
+    want = reference_frames(fb, (6, 6), 3)
+    with Stepper((6, 6), 4096, snapshot_buffers=2) as st:
+        st.upload(fb)
+        st.run_frame_async()          # frame 1
+        st.run_frame_async()          # frame 2 enqueued before frame 1 is read
+        assert st.download(age=1).tobytes() == want[1]
+        st.run_frame_async()          # frame 3
+        assert st.download(age=1).tobytes() == want[2]
+        assert st.download(age=0).tobytes() == want[3]
+    with Stepper((6, 6), 4096) as st:  # one buffer: only the latest snapshot exists
+        st.upload(fb)
+        st.run_frame_async()
+        with pytest.raises(PsimError, match="no snapshot of age 1"):
+            st.download(age=1)
