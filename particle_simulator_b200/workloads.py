@@ -100,3 +100,46 @@ def slab_crystal(rank: int, world: int, storage_factory=None, per_slab: int = 31
             f"cell rows, speeds 1-10 m/s, {1 << geo['grid_log2'][0]}x{1 << geo['grid_log2'][1]} cells, box "
             f"{width * 1e6:.2f}x{height * 1e6:.2f} um; slab {rank} is handed lattice rows [{lo}, {hi})")
     return Workload(f"10M-solid-lattice-per-slab-x{world}", desc, geo["grid_log2"], fb)
+
+
+def clustered_mixed(grid_log2: tuple[int, int] = (10, 10), clusters: int = 6, side: int = 150, gas: int = 20000,
+                    seed: int = 5, lopsided: bool = True) -> Workload:
+    """BASELINE.json configs[4]: mixed-species clustered scene -- liquid-density droplets of species 0 and 1 in a mostly
+    empty box plus a fast gas background of both species (heterogeneous density, load imbalance, high migration
+    rate). Both species are stepped with species-0 parameters, as the reference does (kernel_bucket.cuh:52); `ty` is a
+    label that travels with the particle. `lopsided` puts most droplets in the lower third of the box, so that a row
+    decomposition is badly balanced."""
+    rng = np.random.default_rng(seed)
+    fb = _frame(clusters * side * side + gas, grid_log2, None)
+    # a 300-600 m/s gas needs the shorter step: at the default 50 fs it crosses more than half a cell between two
+    # re-bins and particles meet without ever having interacted (the reference blows up the same way, DESIGN.md 4)
+    fb.metadata["step_dt"] = 10e-15
+    w, h = float(fb.metadata["box_width"]), float(fb.metadata["box_height"])
+    r0 = io.force0_r(fb.metadata)
+    half = 0.5 * side * r0 * 1.05 + 4 * CELL_WIDTH
+    centres: list[tuple[float, float]] = []
+    attempts = 0
+    while len(centres) < clusters:
+        attempts += 1
+        assert attempts < 10000, "the droplets do not fit the box"
+        cx = rng.uniform(half, w - half)
+        top = h / 3 if lopsided and len(centres) < clusters - 1 else h
+        cy = rng.uniform(half, max(top, 2.2 * half) - half) if top > 2 * half else rng.uniform(half, h - half)
+        if all(abs(cx - x) > 2 * half or abs(cy - y) > 2 * half for x, y in centres):
+            centres.append((cx, cy))
+    for k, c in enumerate(centres):
+        io.scene_hex_square(fb, side, side, c, 1.05, 150.0, 250.0, k % 2, seed + 17 * k)
+    if gas:
+        io.scene_gas(fb, gas // 2, 3 * CELL_WIDTH, 3 * r0, 300.0, 600.0, 0, seed + 1000)
+        io.scene_gas(fb, gas - gas // 2, 3 * CELL_WIDTH, 3 * r0, 300.0, 600.0, 1, seed + 1001)
+    desc = (f"{clusters} droplets of {side}x{side} at 1.05 r0 (species alternate), {gas} gas particles at 300-600 m/s, "
+            f"{1 << grid_log2[0]}x{1 << grid_log2[1]} cells")
+    return Workload("mixed-species-clusters", desc, grid_log2, fb)
+
+
+def heat(frame: FrameBuffer, factor: float) -> None:
+    """The heating ramp of BASELINE.json configs[2]: every velocity times `factor`, on the host, between frames
+    (the scene then goes back through the ordinary upload path; the reference has no thermostat)."""
+    p = frame.particles
+    p["vx"] *= np.float32(factor)
+    p["vy"] *= np.float32(factor)
