@@ -298,13 +298,14 @@ __global__ void __launch_bounds__(1024) row_tiles_kernel(const uint32_t* __restr
     }
 }
 
-// One TileC per tile index b in [0, tile_base[own_rows]), and its row of the column-offset table.
+// One TileC per tile index b in [0, tile_base[own_rows]), and its row of the column-offset table. One warp per tile:
+// the lanes share the scan of the band's column counts.
 __global__ void tile_build_kernel(const uint32_t* __restrict__ cell_start, const uint32_t* __restrict__ pad_start,
                                   const uint32_t* __restrict__ tile_base, const uint32_t* __restrict__ couple_i0,
                                   const uint32_t* __restrict__ cell_id, Grid g, TileC* __restrict__ tiles,
                                   uint32_t* __restrict__ col_start) {
-    const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
-    if (b >= tile_base[g.own_rows]) return;
+    const uint32_t b = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31u;
+    if (b >= tile_base[g.own_rows]) return;  // whole warps leave together
     // the last row whose base is <= b (rows without tiles share their successor's base and are skipped over)
     const uint32_t r = (uint32_t)last_le(tile_base, (int)g.own_rows, b);
     const uint32_t row = g.own_row0 + r;
@@ -332,16 +333,24 @@ __global__ void tile_build_kernel(const uint32_t* __restrict__ cell_start, const
         fits = fits && t.cs_cnt[d] <= (uint32_t)kCsRow;
     }
     uint32_t band = 0;
-    if (fits) {
+    if (fits) {  // exclusive scan of the three rows' counts over the band's columns, 32 columns at a time
         uint32_t* col = col_start + (size_t)b * kColStride;
-        for (uint32_t c = 0; c < t.ncol; ++c) {
-            col[c] = band;
-            for (int d = 0; d < 3; ++d)
-                if (has[d]) band += cell_start[lo[d] + c + 1] - cell_start[lo[d] + c];
+        const uint32_t padded = (t.ncol + 1u + 3u) & ~3u;
+        for (uint32_t c0 = 0; c0 < padded; c0 += 32) {
+            const uint32_t c = c0 + lane;
+            uint32_t n = 0;
+            if (c < t.ncol)
+                for (int d = 0; d < 3; ++d)
+                    if (has[d]) n += cell_start[lo[d] + c + 1] - cell_start[lo[d] + c];
+            uint32_t incl = n;
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t u = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+                if (lane >= (uint32_t)o) incl += u;
+            }
+            if (c < padded) col[c] = band + incl - n;  // entries past ncol repeat the total
+            band += __shfl_sync(0xFFFFFFFFu, incl, 31);
         }
-        col[t.ncol] = band;
-        for (uint32_t c = t.ncol + 1; c < ((t.ncol + 1u + 3u) & ~3u); ++c) col[c] = band;
     }
     t.fits = fits && band <= (uint32_t)kBandCap ? 1u : 0u;
-    tiles[b] = t;
+    if (lane == 0) tiles[b] = t;
 }

@@ -1572,7 +1572,7 @@ int bin_phase_tiles(PsimStepper* s) {
     tile_desc_kernel<<<div_up(tiles, 128), 128, 0, s->stream>>>(s->cell_start, s->grid, s->own_lo, s->own_hi, s->tiles);
     s->launches += 1;
     if (s->float_grid && s->n_tiles_c) {
-        tile_build_kernel<<<div_up(s->n_tiles_c, 128), 128, 0, s->stream>>>(s->cell_start, s->pad_start, s->tile_base,
+        tile_build_kernel<<<div_up(s->n_tiles_c, 4), 128, 0, s->stream>>>(s->cell_start, s->pad_start, s->tile_base,
                                                                           s->couple_i0, s->cell_id, s->grid, s->tiles_c,
                                                                           s->col_start);
         s->launches += 1;

@@ -115,3 +115,37 @@ def test_10m_window_single_step_vs_oracle():
         a["x"] >>= np.uint32(3)
         a["y"] >>= np.uint32(3)
     assert_state_close(g, w, b, wfb.metadata, "10M window")
+
+
+def test_100m_liquid_on_one_gpu():
+    """BASELINE.json configs[3]'s size on ONE B200 (the 8-GPU decomposition of the same box is what bench.py --gpus 8
+    runs per slab): 98 M particles at liquid spacing on 8192 x 4096 cells (box 6.4 x 3.2 um, a 2:1 box: the fp32
+    path folds ky/kx = 1/2 into its scale). One frame of 18 steps and a re-bin; conservation and consistency only."""
+    from particle_simulator_b200.stepper import Stepper
+
+    nx, ny, grid = 14000, 7000, (13, 12)
+    n = nx * ny
+    fb = FrameBuffer(n)
+    fb.metadata["box_width"] = 6.4e-6
+    fb.metadata["box_height"] = 3.2e-6
+    fb.metadata["steps_per_frame"] = 18
+    io.scene_hex_square(fb, nx, ny, (3.2e-6, 1.6e-6), 1.05, 1.0, 10.0, 0, seed=4)
+    with Stepper(grid, n) as st:
+        st.upload(fb)
+        assert st.particle_count == n
+        stats = st.tile_stats()
+        assert stats["float_path"] == 1 and stats["tiles_staged"] >= 0.99 * stats["tiles"]
+        cs = st.cell_start()
+        assert cs[0] == 0 and cs[-1] == n and (np.diff(cs.astype(np.int64)) >= 0).all()
+        p0 = np.array([fb.particles["vx"].sum(dtype=np.float64), fb.particles["vy"].sum(dtype=np.float64)])
+        st.run_frame_async()
+        st.sync()
+        assert (st.steps_executed, st.rebins_executed) == (18, 1)
+        out = st.download(fb)  # into the same host buffer
+    assert out.count == n
+    p = out.particles
+    assert (p["ty"] == 0).all() and np.isfinite(p["vx"]).all() and np.isfinite(p["vy"]).all()
+    c = cells_of(p, *grid)
+    assert (np.diff(c) >= -(1 << 13)).all()  # still (nearly) cell-sorted: a snapshot is not freshly binned
+    p1 = np.array([p["vx"].sum(dtype=np.float64), p["vy"].sum(dtype=np.float64)])
+    assert np.abs(p1 - p0).max() < 1e-5 * np.abs(p["vx"]).sum(dtype=np.float64)  # pair forces conserve momentum
