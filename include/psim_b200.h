@@ -100,6 +100,10 @@ int psim_step_async(PsimStepper* s, uint32_t steps);
 int psim_rebin_async(PsimStepper* s);
 /* ... and packing the current state into the snapshot buffer. */
 int psim_snapshot_async(PsimStepper* s);
+/* Decimated snapshots: from now on a snapshot holds every stride-th particle of the cell-sorted state (a spatially
+ * uniform sample for display; at 10 M particles a full frame is 200 MB per snapshot, which is what the reference's
+ * Kernel::read (kernel.cuh:117-129) would move). 1 = every particle (default). The state itself is untouched. */
+int psim_set_snapshot_stride(PsimStepper* s, uint32_t stride);
 
 /* = Kernel::sync (kernel.cuh:88-94). */
 int psim_sync(PsimStepper* s);

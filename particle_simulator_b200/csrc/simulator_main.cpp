@@ -39,12 +39,13 @@ struct Options {
     uint32_t min_capacity = 1u << 16;        // kernel.cuh:20
     bool native_schedule = false;
     bool verbose = false;
+    uint32_t snapshot_stride = 1;            // send every k-th particle only (decimated frames for display)
 };
 
 void usage(const char* argv0) {
     std::fprintf(stderr,
                  "usage: %s [--connect host:port | --files in.bin out.bin] [--device N] [--grid LX LY]\n"
-                 "          [--frames N] [--capacity N] [--native-schedule] [--verbose]\n"
+                 "          [--frames N] [--capacity N] [--snapshot-stride K] [--native-schedule] [--verbose]\n"
                  "Steps particle_io scenes on a B200 and streams snapshots back (drop-in for cuda_simulator).\n",
                  argv0);
 }
@@ -141,7 +142,10 @@ struct Simulator {
     // upload + start the first frame + echo the ingested scene (cuda_simulator.cu:28-31 and :16-20)
     bool start_scene(Frontend& fe, const FrameHeader* scene) {
         if (!fit_to(scene)) return false;
+        if (!check(psim_set_snapshot_stride(stepper, 1), "psim_set_snapshot_stride")) return false;  // the echo is complete
         if (!check(psim_upload_frame(stepper, scene), "psim_upload_frame")) return false;
+        if (!check(psim_set_snapshot_stride(stepper, opt.snapshot_stride ? opt.snapshot_stride : 1), "psim_set_snapshot_stride"))
+            return false;
         out->particle_count = out_capacity;
         if (!check(psim_download_frame(stepper, out), "psim_download_frame")) return false;  // the binned scene
         if (!check(psim_run_frame_async(stepper), "psim_run_frame_async")) return false;
@@ -190,6 +194,7 @@ int main(int argc, char** argv) {
         else if (a == "--grid") { need(2); opt.grid_x_log2 = std::atoi(argv[++i]); opt.grid_y_log2 = std::atoi(argv[++i]); }
         else if (a == "--frames") { need(1); opt.max_frames = std::atol(argv[++i]); }
         else if (a == "--capacity") { need(1); opt.min_capacity = (uint32_t)std::atol(argv[++i]); }
+        else if (a == "--snapshot-stride") { need(1); opt.snapshot_stride = (uint32_t)std::atol(argv[++i]); }
         else if (a == "--native-schedule") opt.native_schedule = true;
         else if (a == "--verbose") opt.verbose = true;
         else { usage(argv[0]); return a == "--help" || a == "-h" ? 0 : 2; }

@@ -194,10 +194,23 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 // CLAMP: the window may contain i itself (own row): r2 is clamped away from 0 so that g stays
 // finite and the zero separation gives an exact 0 (kernel_bucket.cuh:85 skips j == i).
 // ------------------------------------------------------------------------------------------------
-template <int KN, int FRAC, bool ANISO, bool MASK1, bool CLAMP>
+// f_dist for any two particles of the box (particle.cuh:41-47): the unsigned difference can exceed 2^31.
+__device__ __forceinline__ float wide_diff(uint32_t b, uint32_t a) {
+    return a < b ? __uint2float_rn(b - a) : -__uint2float_rn(a - b);
+}
+
+// WIDE: the two particles may be further apart than half the box (all-pairs mode); inside a 3x3 stencil of a
+// grid of >= 8 cells per axis the wrapping signed difference is the separation.
+template <int KN, int FRAC, bool ANISO, bool MASK1, bool CLAMP, bool WIDE = false>
 __device__ __forceinline__ void pair2(uint2 pi, uint2 pj0, uint2 pj1, const Phys& ph, float2& gx, float2& gy) {
-    float2 x = make_float2(__int2float_rn((int)(pj0.x - pi.x)), __int2float_rn((int)(pj1.x - pi.x)));
-    float2 y = make_float2(__int2float_rn((int)(pj0.y - pi.y)), __int2float_rn((int)(pj1.y - pi.y)));
+    float2 x, y;
+    if (WIDE) {
+        x = make_float2(wide_diff(pj0.x, pi.x), wide_diff(pj1.x, pi.x));
+        y = make_float2(wide_diff(pj0.y, pi.y), wide_diff(pj1.y, pi.y));
+    } else {
+        x = make_float2(__int2float_rn((int)(pj0.x - pi.x)), __int2float_rn((int)(pj1.x - pi.x)));
+        y = make_float2(__int2float_rn((int)(pj0.y - pi.y)), __int2float_rn((int)(pj1.y - pi.y)));
+    }
     if (ANISO) y = __fmul2_rn(y, splat(ph.yscale));
     float2 r2 = __ffma2_rn(y, y, __fmul2_rn(x, x));
     r2 = __fmul2_rn(r2, splat(ph.inv_c2));
@@ -540,6 +553,46 @@ __global__ void __launch_bounds__(kTile, 8) step_kernel(const StepArgs a) {
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// DataStructure::CompactArray (kernel_compact.cuh:4-34): every particle interacts with every other one, particles
+// keep their input order, there is no grid. O(N^2): the reference's teaching baseline, offered so that the
+// metadata's data_structure switch (kernel.cuh:143-150) means here what it means there. One thread per particle;
+// the array streams through shared memory 128 positions at a time; same pair arithmetic as step_kernel, with
+// f_dist's unsigned separation (two particles can be more than half the box apart).
+// ------------------------------------------------------------------------------------------------
+template <int KN, int FRAC, bool ANISO>
+__global__ void __launch_bounds__(kTile) allpairs_step_kernel(const StepArgs a) {
+    __shared__ uint2 s_pos[kTile];
+    const uint32_t n = a.own_hi;
+    const uint32_t i = blockIdx.x * kTile + threadIdx.x;
+    const bool live = i < n;
+    const uint2 pi = live ? a.pos_in[i] : make_uint2(0, 0);
+    float2 gx = splat(0.f), gy = splat(0.f);
+    for (uint32_t base = 0; base < n; base += kTile) {
+        __syncthreads();
+        if (base + threadIdx.x < n) s_pos[threadIdx.x] = a.pos_in[base + threadIdx.x];
+        __syncthreads();
+        const int count = (int)min((uint32_t)kTile, n - base);
+        int k = 0;
+        for (; k + 1 < count; k += 2)  // j == i contributes an exact 0 (the clamp), like the reference's `continue`
+            pair2<KN, FRAC, ANISO, false, true, true>(pi, s_pos[k], s_pos[k + 1], a.ph, gx, gy);
+        if (k < count) pair2<KN, FRAC, ANISO, true, true, true>(pi, s_pos[k], pi, a.ph, gx, gy);
+    }
+    if (live) finish_particle(i, pi, a.vel[i], gx.x + gx.y, gy.x + gy.y, a.ph.pair_scale, a.ph.pair_scale_y, a);
+}
+
+// CompactArray ingest: wire-format records (already free of nulls) -> the structure of arrays, input order kept.
+__global__ void unpack_kernel(const Particle* __restrict__ rec, uint32_t n, uint2* __restrict__ pos,
+                              float2* __restrict__ vel, int32_t* __restrict__ ty, uint32_t* __restrict__ cell_id) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const Particle q = rec[i];
+    pos[i] = make_uint2(q.x, q.y);
+    vel[i] = make_float2(q.vx, q.vy);
+    ty[i] = q.ty;
+    cell_id[i] = 0;
+}
+
 #include "step_float.cuh"
 
 // ------------------------------------------------------------------------------------------------
@@ -815,10 +868,15 @@ __global__ void tile_desc_kernel(const uint32_t* __restrict__ cell_start, Grid g
 }
 
 // snapshot: pack the owned particles back into wire-format records (particle.rs:10-18)
+// With stride > 1 only every stride-th particle of the (cell-sorted, hence spatially coherent) state is packed: a
+// decimated snapshot for display, 1/stride of the bytes to copy out and send.
 __global__ void pack_kernel(const uint2* __restrict__ pos, const float2* __restrict__ vel,
-                            const int32_t* __restrict__ ty, uint32_t lo, uint32_t hi, Particle* __restrict__ out) {
-    uint32_t i = lo + blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= hi) return;
+                            const int32_t* __restrict__ ty, uint32_t lo, uint32_t hi, uint32_t stride,
+                            Particle* __restrict__ out) {
+    const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint64_t i64 = (uint64_t)lo + (uint64_t)k * stride;
+    if (i64 >= hi) return;
+    const uint32_t i = (uint32_t)i64;
     uint2 p = pos[i];
     float2 v = vel[i];
     Particle q;
@@ -827,7 +885,7 @@ __global__ void pack_kernel(const uint2* __restrict__ pos, const float2* __restr
     q.vx = v.x;
     q.vy = v.y;
     q.ty = ty[i];
-    out[i - lo] = q;
+    out[k] = q;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -959,6 +1017,7 @@ struct PsimStepper {
     // Snapshots: one buffer, or two that alternate (PsimConfig.snapshot_buffers = 2) so that the previous
     // frame's snapshot can be copied out while the next frame, pack included, is already enqueued.
     int nsnap = 1, snap_latest = 0;
+    uint32_t snapshot_stride = 1;  // snapshots hold every stride-th particle
     uint64_t snaps_taken = 0;
     cudaEvent_t snapshot_ready[2] = {nullptr, nullptr};
     cudaEvent_t snapshot_consumed[2] = {nullptr, nullptr};
@@ -1020,6 +1079,7 @@ struct PsimStepper {
 
     uint32_t snapshot_n[2] = {0, 0};
     FrameMetadata snapshot_meta[2]{};
+    bool compact_mode = false;  // the scene was uploaded with DataStructure::CompactArray: all-pairs steps, no grid
     bool has_scene = false;
     bool has_snapshot = false;
     bool fresh_scene = false;  // nothing has been stepped since the ingest: the binning is current
@@ -1271,7 +1331,24 @@ void launch_step_c(PsimStepper* s, const StepArgs& a) {
     else step_kernel_c<KN, kFracPoly><<<s->n_tiles_c, kCouples, 0, s->stream>>>(a, ac);
 }
 
+template <int KN, int FRAC>
+void launch_allpairs_aniso(PsimStepper* s, const StepArgs& a, uint32_t tiles) {
+    if (s->kernel_aniso) allpairs_step_kernel<KN, FRAC, true><<<tiles, kTile, 0, s->stream>>>(a);
+    else allpairs_step_kernel<KN, FRAC, false><<<tiles, kTile, 0, s->stream>>>(a);
+}
+
+// All-pairs mode keeps two variants: the default exponents' fast path and the general one.
+void launch_allpairs(PsimStepper* s, const StepArgs& a, uint32_t tiles) {
+    if (s->kernel_kn == 8 && s->kernel_frac == kFracPoly) launch_allpairs_aniso<8, kFracPoly>(s, a, tiles);
+    else if (s->kernel_kn == 8 && s->kernel_frac == kFracNone) launch_allpairs_aniso<8, kFracNone>(s, a, tiles);
+    else launch_allpairs_aniso<0, kFracEx2>(s, a, tiles);
+}
+
 void launch_step(PsimStepper* s, const StepArgs& a, uint32_t tiles) {
+    if (s->compact_mode) {
+        launch_allpairs(s, a, tiles);
+        return;
+    }
     if (s->float_path) {
         switch (s->kernel_kn) {
             case 5: launch_step_c<5>(s, a); break;
@@ -1584,6 +1661,7 @@ int bin_phase_tiles(PsimStepper* s) {
 // Bin all slabs of the team: an ingested frame (`ingest`: `records`/`count` in device memory), or the
 // live state (bucket_move, kernel_bucket.cuh:5-39) including migration between slabs.
 int team_bin(const Team& t, bool ingest, const Particle* records, uint32_t count) {
+    if (!ingest && t.ranks[0]->compact_mode) return PSIM_OK;  // CompactArray: there is no grid to re-bin into
     const bool slabs = t.ranks[0]->nranks > 1;
     std::vector<XferOp> ops(t.count);
     int rc;
@@ -1740,14 +1818,15 @@ int enqueue_snapshot(PsimStepper* s) {
     const int k = s->snaps_taken ? (s->snap_latest + 1) % s->nsnap : 0;
     // the snapshot that lived in this buffer must have left it before it is overwritten
     CK(cudaStreamWaitEvent(s->stream, s->snapshot_consumed[k], 0));
-    if (s->n) {
-        pack_kernel<<<div_up(s->n, 256), 256, 0, s->stream>>>(s->pos[s->cur_pos], s->vel[s->cur_vel], s->ty[s->cur_ty],
-                                                              s->own_lo, s->own_hi, s->snapshot[k]);
+    const uint32_t packed = div_up(s->n, s->snapshot_stride);
+    if (packed) {
+        pack_kernel<<<div_up(packed, 256), 256, 0, s->stream>>>(s->pos[s->cur_pos], s->vel[s->cur_vel], s->ty[s->cur_ty],
+                                                                s->own_lo, s->own_hi, s->snapshot_stride, s->snapshot[k]);
         s->launches += 1;
         CK(cudaGetLastError());
     }
     CK(cudaEventRecord(s->snapshot_ready[k], s->stream));
-    s->snapshot_n[k] = s->n;
+    s->snapshot_n[k] = packed;
     s->snapshot_meta[k] = s->meta;
     s->snap_latest = k;
     s->snaps_taken += 1;
@@ -1775,6 +1854,7 @@ int collect_timing(PsimStepper* s) {
 
 // Bin `count` wire-format records that sit in device memory at `records`, on every slab of the team.
 int team_ingest(const Team& t, const Particle* records, uint32_t count) {
+    for (int r = 0; r < t.count; ++r) t.ranks[r]->compact_mode = false;
     int rc = team_bin(t, true, records, count);
     if (rc) return rc;
     for (int r = 0; r < t.count; ++r) {
@@ -1798,7 +1878,13 @@ int team_run_frame(const Team& t) {
     PsimStepper* lead = t.ranks[0];
     const uint32_t target = lead->meta.steps_per_frame;
     int rc;
-    if (lead->cfg.schedule == PSIM_SCHEDULE_REFERENCE) {
+    if (lead->compact_mode) {
+        // compact_kernel_run_async, kernel_compact.cuh:78-92: steps_per_frame steps (two when it is 0: the even
+        // branch runs its pair of steps unconditionally)
+        const uint32_t steps = target == 0 ? 2u : target;
+        for (uint32_t k = 0; k < steps; ++k)
+            if ((rc = team_step(t))) return rc;
+    } else if (lead->cfg.schedule == PSIM_SCHEDULE_REFERENCE) {
         // bucket_kernel_run_async, kernel_bucket.cuh:181-206: the reference always runs one step,
         // then alternates "re-bin + 1 step" with pairs of steps, 16 steps between re-bins counted
         // from the first re-bin, the countdown restarting with every frame. Pairs make it overshoot
@@ -2197,11 +2283,63 @@ int psim_comm_init(PsimStepper* s, const void* unique_id128) {
 
 int psim_halo_mode(const PsimStepper* s) { return s ? (s->nranks == 1 ? 0 : (s->push ? 2 : 1)) : 0; }
 
+}  // extern "C"
+
+namespace {
+// Scene ingest for DataStructure::CompactArray = frame_compact_into (kernel.cuh:207-209): the live records in input
+// order, no binning. The null records are dropped on the host, as the reference does.
+int upload_compact(PsimStepper* s, const FrameHeader* frame) {
+    if (s->nranks > 1 || s->group)
+        return fail(s, PSIM_EINVAL, "DataStructure::CompactArray (all pairs) cannot be decomposed into slabs");
+    std::vector<Particle> live;
+    const Particle* rec = frame->particles;
+    uint32_t n = frame->particle_count;
+    bool has_null = false;
+    for (uint32_t i = 0; i < n && !has_null; ++i) has_null = rec[i].ty < 0;
+    if (has_null) {
+        live.reserve(n);
+        for (uint32_t i = 0; i < n; ++i)
+            if (rec[i].ty >= 0) live.push_back(rec[i]);
+        rec = live.data();
+        n = (uint32_t)live.size();
+    }
+    if (n > s->cfg.max_particles)
+        return fail(s, PSIM_ECAPACITY, "%u live particles exceed max_particles = %u", n, s->cfg.max_particles);
+    CK(cudaStreamSynchronize(s->stream));
+    CK(cudaStreamSynchronize(s->copy_stream));
+    apply_metadata(s, frame->metadata);
+    s->compact_mode = true;
+    s->cur_pos = s->cur_vel = s->cur_ty = 0;
+    if (n) {
+        CK(cudaMemcpyAsync(s->staging, rec, sizeof(Particle) * (size_t)n, cudaMemcpyHostToDevice, s->stream));
+        unpack_kernel<<<div_up(n, 256), 256, 0, s->stream>>>(s->staging, n, s->pos[0], s->vel[0], s->ty[0], s->cell_id);
+        s->launches += 1;
+        CK(cudaGetLastError());
+    }
+    s->n = s->n_total = s->own_hi = s->b_hi_start = n;
+    s->own_lo = s->b_lo_end = 0;
+    s->has_scene = true;
+    s->fresh_scene = true;
+    s->native_countdown = 0;
+    int rc = enqueue_snapshot(s);
+    if (rc) return rc;
+    CK(cudaStreamSynchronize(s->stream));  // `live` and the caller's frame are free again
+    return PSIM_OK;
+}
+}  // namespace
+
+extern "C" {
+
 int psim_upload_frame(PsimStepper* s, const FrameHeader* frame) {
     if (!s || !frame) return PSIM_EINVAL;
     int rc = check_lone(s, "psim_upload_frame");
     if (rc) return rc;
     CK(cudaSetDevice(s->device));
+    if (frame->metadata.data_structure == 0 /* DataStructure::CompactArray */) {
+        if (frame->particle_count > s->ingest_cap)
+            return fail(s, PSIM_ECAPACITY, "frame holds %u particles, the ingest buffer %u", frame->particle_count, s->ingest_cap);
+        return upload_compact(s, frame);
+    }
     if (frame->particle_count > s->ingest_cap)
         return fail(s, PSIM_ECAPACITY, "frame holds %u particles, the ingest buffer %u (max_particles / ingest_capacity)",
                     frame->particle_count, s->ingest_cap);
@@ -2219,6 +2357,8 @@ int psim_upload_device(PsimStepper* s, const FrameMetadata* meta, const void* d_
     int rc = check_lone(s, "psim_upload_device");
     if (rc) return rc;
     CK(cudaSetDevice(s->device));
+    if (meta->data_structure == 0)
+        return fail(s, PSIM_EINVAL, "psim_upload_device: DataStructure::CompactArray scenes are uploaded from the host");
     if (count > s->ingest_cap)
         return fail(s, PSIM_ECAPACITY, "%u particles, the ingest buffer holds %u", count, s->ingest_cap);
     CK(cudaStreamSynchronize(s->stream));
@@ -2263,6 +2403,13 @@ int psim_rebin_async(PsimStepper* s) {
     CK(cudaSetDevice(s->device));
     s->fresh_scene = false;
     return team_bin(lone(&s), false, nullptr, 0);
+}
+
+int psim_set_snapshot_stride(PsimStepper* s, uint32_t stride) {
+    if (!s) return PSIM_EINVAL;
+    if (stride == 0) return fail(s, PSIM_EINVAL, "psim_set_snapshot_stride: stride must be >= 1");
+    s->snapshot_stride = stride;
+    return PSIM_OK;
 }
 
 int psim_snapshot_async(PsimStepper* s) {
@@ -2364,6 +2511,12 @@ int psim_tile_stats(PsimStepper* s, PsimTileStats* out) {
     std::memset(out, 0, sizeof *out);
     CK(cudaSetDevice(s->device));
     CK(cudaStreamSynchronize(s->stream));
+    if (s->compact_mode) {  // all pairs: plain tiles of 128 particles, nothing staged per tile
+        out->tiles = div_up(s->n, kTile);
+        out->threads_live = s->n;
+        out->threads_launched = (uint64_t)out->tiles * kTile;
+        return PSIM_OK;
+    }
     out->float_path = s->float_path ? 1u : 0u;
     if (s->float_path) {
         std::vector<TileC> t(s->n_tiles_c);
@@ -2492,6 +2645,8 @@ int psim_group_upload_frame(PsimGroup* g, const FrameHeader* frame) {
     if (!g || !frame) return PSIM_EINVAL;
     g->error.clear();
     PsimStepper* s = g->ranks[0];
+    if (frame->metadata.data_structure == 0)
+        return group_fail(g, fail(s, PSIM_EINVAL, "DataStructure::CompactArray (all pairs) cannot be decomposed into slabs"));
     for (PsimStepper* m : g->ranks) m->error.clear();
     CK(cudaSetDevice(s->device));
     if (frame->particle_count > s->ingest_cap)

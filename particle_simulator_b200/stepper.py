@@ -90,6 +90,7 @@ def lib() -> ctypes.CDLL:
             "psim_step_async": [vp, ctypes.c_uint32],
             "psim_rebin_async": [vp],
             "psim_snapshot_async": [vp],
+            "psim_set_snapshot_stride": [vp, ctypes.c_uint32],
             "psim_sync": [vp],
             "psim_download_frame": [vp, vp],
             "psim_download_frame_ex": [vp, ctypes.c_uint32, vp],
@@ -210,6 +211,10 @@ class Stepper:
 
     def snapshot_async(self) -> None:
         self._check(lib().psim_snapshot_async(self._h))
+
+    def set_snapshot_stride(self, stride: int) -> None:
+        """Snapshots hold every `stride`-th particle from now on (decimated frames for display)."""
+        self._check(lib().psim_set_snapshot_stride(self._h, stride))
 
     def sync(self) -> None:
         self._check(lib().psim_sync(self._h))

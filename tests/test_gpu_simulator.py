@@ -164,3 +164,26 @@ def test_previous_snapshot_can_be_downloaded_while_the_next_frame_is_enqueued(go
         st.run_frame_async()
         with pytest.raises(PsimError, match="no snapshot of age 1"):
             st.download(age=1)
+
+
+def test_decimated_snapshots(golden):
+    """psim_set_snapshot_stride: every k-th particle of the cell-sorted state, the state itself untouched."""
+    from particle_simulator_b200.stepper import PsimError, Stepper
+
+    g = golden("liquid4k")
+    meta = g["meta"][0].copy()
+    meta["steps_per_frame"] = 18
+    fb = frame_from(g["input"], meta)
+    with Stepper((6, 6), 8192) as st:
+        st.upload(fb)
+        st.run_frame_async()
+        full = st.download().particles.copy()
+        for stride in (3, 7, 5000):
+            st.set_snapshot_stride(stride)
+            st.snapshot_async()
+            assert st.download().particles.tobytes() == full[::stride].tobytes()
+        st.set_snapshot_stride(1)
+        st.snapshot_async()
+        assert st.download().particles.tobytes() == full.tobytes()
+        with pytest.raises(PsimError, match="stride"):
+            st.set_snapshot_stride(0)
