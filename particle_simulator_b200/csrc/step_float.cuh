@@ -113,13 +113,14 @@ __global__ void __launch_bounds__(kCouples, 9) step_kernel_c(const StepArgs a, c
 
     const Grid& g = a.g;
     const PhysF& pf = ac.pf;
-    const TileC t = ac.tiles[blockIdx.x];
+    const uint32_t tile = halo_tile_order(a, blockIdx.x, gridDim.x);
+    const TileC t = ac.tiles[tile];
     const bool live = threadIdx.x < t.nk;
 
     if (a.push) {  // uniform over the grid
         if (threadIdx.x == 0) {
             if (blockIdx.x == 0) halo_publish_empty(a);
-            halo_wait(a, blockIdx.x);
+            halo_wait(a, tile);
         }
         if (!t.fits) __syncthreads();  // the global-memory path reads the ghost rows directly
     }
@@ -143,7 +144,7 @@ __global__ void __launch_bounds__(kCouples, 9) step_kernel_c(const StepArgs a, c
 #pragma unroll
         for (int d = 0; d < 3; ++d)
             if (t.cs_cnt[d]) bulk_copy_g2s(s_cs[d], a.cell_start + t.cs_lo[d], t.cs_cnt[d] * 4u, &s_bar);
-        bulk_copy_g2s(s_col, ac.col_start + (size_t)blockIdx.x * kColStride, col_bytes, &s_bar);
+        bulk_copy_g2s(s_col, ac.col_start + (size_t)tile * kColStride, col_bytes, &s_bar);
     }
 
     // this thread's couple (the loads fly while the slices arrive)

@@ -457,6 +457,17 @@ __device__ __forceinline__ void halo_push(const StepArgs& a, uint32_t i, uint2 p
     }
 }
 
+// Which tile the b-th CTA of the grid steps. With a pushed halo the tiles of BOTH boundary rows come first (the first
+// owned row's, then the last owned row's, then the interior in order): the halo is on the wire, fenced and published
+// while the interior computes, and no neighbour ever finds a flag late because its producer ran at the grid's tail.
+__device__ __forceinline__ uint32_t halo_tile_order(const StepArgs& a, uint32_t b, uint32_t tiles) {
+    if (!a.push) return b;
+    const uint32_t lo = a.h.lo_tiles, hi0 = max(a.h.hi_tile0, lo), hi_count = tiles - min(hi0, tiles);
+    if (b < lo) return b;
+    if (b < lo + hi_count) return hi0 + (b - lo);
+    return b - hi_count;
+}
+
 // A slab without particles still owes its neighbours the epoch of every step.
 __global__ void halo_publish_kernel(StepArgs a) {
     if (threadIdx.x == 0 && blockIdx.x == 0) halo_publish_empty(a);
@@ -503,13 +514,13 @@ __global__ void __launch_bounds__(kTile, 8) step_kernel(const StepArgs a) {
     __shared__ __align__(16) uint2 s_pos[3][kPosCap];
     __shared__ __align__(8) uint64_t s_bar;
 
-    const uint32_t b = blockIdx.x;
+    const uint32_t b = halo_tile_order(a, blockIdx.x, gridDim.x);
     const uint32_t i = a.own_lo + b * kTile + threadIdx.x;
     const TileDesc t = a.tiles[b];
 
     if (a.push) {  // uniform over the grid
         if (threadIdx.x == 0) {
-            if (b == 0) halo_publish_empty(a);
+            if (blockIdx.x == 0) halo_publish_empty(a);
             halo_wait(a, b);
         }
         if (!t.fits) __syncthreads();  // the global-memory path reads the ghost rows directly
