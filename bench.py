@@ -216,14 +216,14 @@ def run_ours(args, rank: int, world: int, local_rank: int) -> None:
     stream = torch.cuda.Stream()
     if world == 1:
         wl = workloads.config_10m_solid(storage=pinned_frame_storage(3162 * 3163))
-        st = Stepper(wl.grid_log2, wl.particles, device=local_rank)
+        st = Stepper(wl.grid_log2, wl.particles, device=local_rank, snapshot_buffers=2)
     else:
         # weak scaling: one crystal across `world` slabs of 2048 cell rows, ~10M particles per slab; rank r
         # steps slab r, halo rows and migrants travel over NCCL send/recv (NVLink)
         wl = workloads.slab_crystal(rank, world, storage_factory=pinned_frame_storage)
         uid = slabs.broadcast_bytes(dist, Stepper.comm_unique_id() if rank == 0 else None, 128, device=dev)
         st = Stepper(wl.grid_log2, int(1.05 * 3162 * 3163), device=local_rank, slab_rank=rank, slab_count=world,
-                     ingest_capacity=wl.frame.count)
+                     ingest_capacity=wl.frame.count, snapshot_buffers=2)
         st.comm_init(uid)
     halo = {0: "none (single slab)", 1: "ncclSend/ncclRecv after every step",
             2: "pushed by the step kernel over NVLink peer memory (CUDA IPC), epoch flags"}[st.halo_mode]
@@ -267,19 +267,41 @@ def run_ours(args, rank: int, world: int, local_rank: int) -> None:
     value = n * steps_done / (ms * 1e-3)
 
     # ---- end-to-end leg: host frame in, host frame out, every step -------------------------------
-    for _ in range(min(args.warmup, 2)):
-        st.upload(wl.frame)
-        st.run_frame_async()
-        st.download(out)
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        st.upload(wl.frame)
-        st.run_frame_async()
-        st.download(out)
-    torch.cuda.synchronize()
-    t_e2e = time.perf_counter() - t0
-    t_e2e = over_ranks(t_e2e, "max")
+    # Pipelined through the public API: every step uploads its scene from page-locked host memory
+    # (psim_stage_frame_async + psim_upload_staged) and downloads its result (psim_download_frame_begin / _end); the
+    # copies of steps k+1 and k-1 run on their own streams while step k's frame is computed.
+    def e2e_pipelined(steps: int) -> float:
+        barrier()
+        t0 = time.perf_counter()
+        st.stage_async(wl.frame)
+        pending = False
+        for k in range(steps):
+            st.upload_staged()
+            if k + 1 < steps:
+                st.stage_async(wl.frame)
+            st.run_frame_async()
+            if pending:
+                st.download_end()
+            st.download_begin(out)
+            pending = True
+        st.download_end()
+        torch.cuda.synchronize()
+        return time.perf_counter() - t0
+
+    # ... and one call after the other (upload, frame, download), nothing overlapped, for comparison
+    def e2e_synchronous(steps: int) -> float:
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            st.upload(wl.frame)
+            st.run_frame_async()
+            st.download(out)
+        torch.cuda.synchronize()
+        return time.perf_counter() - t0
+
+    e2e_pipelined(min(args.warmup, 2))
+    t_e2e = over_ranks(e2e_pipelined(args.steps), "max")
+    t_e2e_sync = over_ranks(e2e_synchronous(args.steps), "max")
     assert int(over_ranks(float(out.count), "sum")) == n  # nothing lost, whatever slab holds it now
     e2e_value = n * executed * args.steps / t_e2e
     h2d = int(over_ranks(float(packet_size(wl.frame.count)), "sum"))
@@ -312,7 +334,11 @@ def run_ours(args, rank: int, world: int, local_rank: int) -> None:
                          "kernel_ms": kernel_ms, "kernel_ms_max_over_ranks": kernel_ms_max, "kernel_launches_timed": step_launches,
                          "kernel_share_of_step": step_ms / ms},
             "e2e": {"value": e2e_value, "unit": "particle-updates/s", "h2d_bytes_per_step": h2d,
-                    "d2h_bytes_per_step": d2h, "ms_per_step": 1e3 * t_e2e / args.steps},
+                    "d2h_bytes_per_step": d2h, "ms_per_step": 1e3 * t_e2e / args.steps,
+                    "how": "every step: scene uploaded from page-locked host memory, binned, one frame, snapshot "
+                           "downloaded; the copies of steps k+1 / k-1 overlap step k's frame "
+                           "(psim_stage_frame_async, psim_upload_staged, psim_download_frame_begin/_end)",
+                    "synchronous_ms_per_step": 1e3 * t_e2e_sync / args.steps},
             "gpu_launches": launches,
             "host_enqueue_ms_per_step": 1e3 * t_host / args.steps,
             "clocks": clocks,

@@ -117,6 +117,21 @@ int psim_download_frame(PsimStepper* s, FrameHeader* dst);
  * (needs PsimConfig.snapshot_buffers = 2). */
 int psim_download_frame_ex(PsimStepper* s, uint32_t age, FrameHeader* dst);
 
+/* Pipelined frames (streaming scenes at full PCIe duplex): the copies run on their own streams while frames compute.
+ *   psim_stage_frame_async   starts the host-to-device copy of `frame` into a second ingest buffer and returns; the
+ *                            frame's memory (page-locked for a real overlap) must stay untouched until
+ *                            psim_upload_staged has returned;
+ *   psim_upload_staged       = psim_upload_frame of the staged frame, minus the copy: bins it as soon as it has
+ *                            arrived and the work enqueued so far has finished;
+ *   psim_download_frame_begin starts the device-to-host copy of a snapshot (age as psim_download_frame_ex) and returns;
+ *                            the header of `dst` is valid at once, the records after psim_download_frame_end.
+ * With PsimConfig.snapshot_buffers = 2 the loop  upload_staged(k); stage(k+1); run_frame_async(k); download_end(k-1);
+ * download_begin(k)  moves frame k+1 in and frame k-1 out while frame k is stepped (bench.py's e2e leg). */
+int psim_stage_frame_async(PsimStepper* s, const FrameHeader* frame);
+int psim_upload_staged(PsimStepper* s);
+int psim_download_frame_begin(PsimStepper* s, uint32_t age, FrameHeader* dst);
+int psim_download_frame_end(PsimStepper* s);
+
 /* Page-locked host memory for frames (uploads and downloads from pageable memory are staged by the driver
  * and run at a fraction of the link rate). NULL on failure. */
 void* psim_host_alloc(size_t bytes);

@@ -1063,6 +1063,17 @@ struct PsimStepper {
     uint32_t* rank_in_cell = nullptr;
     uint32_t* perm = nullptr;
     Particle* staging = nullptr;   // ingest buffer (wire-format records)
+    // pipelined ingest (psim_stage_frame_async / psim_upload_staged): a second ingest buffer filled over its own
+    // stream while the running frame computes
+    Particle* staging_async = nullptr;
+    cudaStream_t h2d_stream = nullptr;
+    cudaEvent_t staged_ready = nullptr;
+    FrameMetadata staged_meta{};
+    uint32_t staged_count = 0;
+    bool has_staged = false;
+    // pipelined download (psim_download_frame_begin / _end)
+    FrameHeader* pending_dst = nullptr;
+    int pending_k = -1;
     Particle* snapshot[2] = {nullptr, nullptr};  // packed snapshots of the owned particles (wire-format records)
     uint32_t ingest_cap = 0;       // records the ingest buffer holds
     unsigned char* outbox[2] = {nullptr, nullptr};
@@ -2030,6 +2041,9 @@ void psim_destroy(PsimStepper* s) {
     cudaFree(s->cell_id);
     cudaFree(s->tiles);
     cudaFree(s->staging);
+    cudaFree(s->staging_async);
+    if (s->h2d_stream) cudaStreamDestroy(s->h2d_stream);
+    if (s->staged_ready) cudaEventDestroy(s->staged_ready);
     cudaFree(s->snapshot[0]);
     cudaFree(s->snapshot[1]);
     cudaFree(s->mig_counters);
@@ -2381,6 +2395,45 @@ int psim_upload_device(PsimStepper* s, const FrameMetadata* meta, const void* d_
     return team_ingest(lone(&s), s->staging, count);
 }
 
+int psim_stage_frame_async(PsimStepper* s, const FrameHeader* frame) {
+    if (!s || !frame) return PSIM_EINVAL;
+    int rc = check_lone(s, "psim_stage_frame_async");
+    if (rc) return rc;
+    CK(cudaSetDevice(s->device));
+    if (frame->metadata.data_structure == 0)
+        return fail(s, PSIM_EINVAL, "psim_stage_frame_async: DataStructure::CompactArray scenes use psim_upload_frame");
+    if (frame->particle_count > s->ingest_cap)
+        return fail(s, PSIM_ECAPACITY, "frame holds %u particles, the ingest buffer %u (max_particles / ingest_capacity)",
+                    frame->particle_count, s->ingest_cap);
+    if (!s->staging_async) {
+        CK(cudaMalloc(&s->staging_async, sizeof(Particle) * (size_t)s->ingest_cap));
+        CK(cudaStreamCreateWithFlags(&s->h2d_stream, cudaStreamNonBlocking));
+        CK(cudaEventCreateWithFlags(&s->staged_ready, cudaEventDisableTiming));
+    }
+    // the buffer is free: the ingest that read it last returned only after its kernels had finished
+    if (frame->particle_count)
+        CK(cudaMemcpyAsync(s->staging_async, frame->particles, sizeof(Particle) * (size_t)frame->particle_count,
+                           cudaMemcpyHostToDevice, s->h2d_stream));
+    CK(cudaEventRecord(s->staged_ready, s->h2d_stream));
+    s->staged_meta = frame->metadata;
+    s->staged_count = frame->particle_count;
+    s->has_staged = true;
+    return PSIM_OK;
+}
+
+int psim_upload_staged(PsimStepper* s) {
+    if (!s) return PSIM_EINVAL;
+    int rc = check_lone(s, "psim_upload_staged");
+    if (rc) return rc;
+    if (!s->has_staged) return fail(s, PSIM_ESTATE, "psim_upload_staged: no frame has been staged");
+    CK(cudaSetDevice(s->device));
+    CK(cudaStreamWaitEvent(s->stream, s->staged_ready, 0));
+    s->has_staged = false;
+    std::swap(s->staging, s->staging_async);  // the next psim_stage_frame_async fills the other buffer
+    apply_metadata(s, s->staged_meta);
+    return team_ingest(lone(&s), s->staging, s->staged_count);
+}
+
 int psim_set_metadata(PsimStepper* s, const FrameMetadata* meta) {
     if (!s || !meta) return PSIM_EINVAL;
     apply_metadata(s, *meta);  // captured by value at the next enqueue, like kernel_bucket.cuh:121
@@ -2466,6 +2519,37 @@ int psim_download_frame_ex(PsimStepper* s, uint32_t age, FrameHeader* dst) {
 }
 
 int psim_download_frame(PsimStepper* s, FrameHeader* dst) { return psim_download_frame_ex(s, 0, dst); }
+
+int psim_download_frame_begin(PsimStepper* s, uint32_t age, FrameHeader* dst) {
+    if (!s || !dst) return PSIM_EINVAL;
+    if (s->pending_dst) return fail(s, PSIM_ESTATE, "psim_download_frame_begin: a download is already in flight");
+    const int k = snapshot_index(s, age);
+    if (k < 0)
+        return fail(s, PSIM_ESTATE, "psim_download_frame_begin: no snapshot of age %u (%llu packed so far, %d buffer%s)",
+                    age, (unsigned long long)s->snaps_taken, s->nsnap, s->nsnap > 1 ? "s" : "");
+    CK(cudaSetDevice(s->device));
+    if (dst->particle_count < s->snapshot_n[k])
+        return fail(s, PSIM_ECAPACITY, "psim_download_frame_begin: destination holds %u particles, snapshot has %u",
+                    dst->particle_count, s->snapshot_n[k]);
+    CK(cudaStreamWaitEvent(s->copy_stream, s->snapshot_ready[k], 0));
+    if (s->snapshot_n[k])
+        CK(cudaMemcpyAsync(dst->particles, s->snapshot[k], sizeof(Particle) * (size_t)s->snapshot_n[k],
+                           cudaMemcpyDeviceToHost, s->copy_stream));
+    CK(cudaEventRecord(s->snapshot_consumed[k], s->copy_stream));
+    write_header(dst, s->snapshot_meta[k], s->snapshot_n[k]);  // the header is host data: valid at once
+    s->pending_dst = dst;
+    s->pending_k = k;
+    return PSIM_OK;
+}
+
+int psim_download_frame_end(PsimStepper* s) {
+    if (!s) return PSIM_EINVAL;
+    if (!s->pending_dst) return fail(s, PSIM_ESTATE, "psim_download_frame_end: no download in flight");
+    CK(cudaSetDevice(s->device));
+    s->pending_dst = nullptr;
+    CK(cudaStreamSynchronize(s->copy_stream));
+    return PSIM_OK;
+}
 
 void* psim_host_alloc(size_t bytes) {
     void* p = nullptr;

@@ -94,6 +94,10 @@ def lib() -> ctypes.CDLL:
             "psim_sync": [vp],
             "psim_download_frame": [vp, vp],
             "psim_download_frame_ex": [vp, ctypes.c_uint32, vp],
+            "psim_stage_frame_async": [vp, vp],
+            "psim_upload_staged": [vp],
+            "psim_download_frame_begin": [vp, ctypes.c_uint32, vp],
+            "psim_download_frame_end": [vp],
             "psim_get_cell_start": [vp, vp],
             "psim_enable_step_timing": [vp, ctypes.c_int],
             "psim_get_step_timing": [vp, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_uint64)],
@@ -226,6 +230,21 @@ class Stepper:
         frame.count = frame.capacity
         self._check(lib().psim_download_frame_ex(self._h, age, frame.ptr))
         return frame
+
+    # -- pipelined frames: copies on their own streams while frames compute --------------------
+    def stage_async(self, frame: FrameBuffer) -> None:
+        """Start the host-to-device copy of `frame`; keep it untouched until upload_staged() has returned."""
+        self._check(lib().psim_stage_frame_async(self._h, frame.ptr))
+
+    def upload_staged(self) -> None:
+        self._check(lib().psim_upload_staged(self._h))
+
+    def download_begin(self, frame: FrameBuffer, age: int = 0) -> None:
+        frame.count = frame.capacity
+        self._check(lib().psim_download_frame_begin(self._h, age, frame.ptr))
+
+    def download_end(self) -> None:
+        self._check(lib().psim_download_frame_end(self._h))
 
     # -- slab decomposition, one process per slab (NCCL) -------------------------------------
     @staticmethod

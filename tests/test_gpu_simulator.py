@@ -187,3 +187,37 @@ def test_decimated_snapshots(golden):
         assert st.download().particles.tobytes() == full.tobytes()
         with pytest.raises(PsimError, match="stride"):
             st.set_snapshot_stride(0)
+
+
+def test_pipelined_frames_equal_synchronous_ones(golden):
+    """psim_stage_frame_async / psim_upload_staged / psim_download_frame_begin / _end: the loop bench.py's e2e leg runs.
+    Different scenes go in back to back; every result equals the one the synchronous calls give."""
+    from particle_simulator_b200.stepper import PsimError, Stepper
+
+    scenes = []
+    for name, steps in (("hex2500", 18), ("liquid4k", 35), ("gas10k", 18), ("hex2500", 5)):
+        g = golden(name)
+        meta = g["meta"][0].copy()
+        meta["steps_per_frame"] = steps
+        scenes.append(frame_from(g["input"], meta))
+    want = [reference_frames(fb, (6, 6), 1)[1] for fb in scenes]
+    got = []
+    outs = [FrameBuffer(16384), FrameBuffer(16384)]
+    with Stepper((6, 6), 16384, snapshot_buffers=2) as st:
+        with pytest.raises(PsimError, match="no frame has been staged"):
+            st.upload_staged()
+        st.stage_async(scenes[0])
+        for k in range(len(scenes)):
+            st.upload_staged()
+            if k + 1 < len(scenes):
+                st.stage_async(scenes[k + 1])
+            st.run_frame_async()
+            if k:
+                st.download_end()
+                got.append(outs[(k - 1) & 1].tobytes())
+            st.download_begin(outs[k & 1])
+            with pytest.raises(PsimError, match="already in flight"):
+                st.download_begin(FrameBuffer(16384))
+        st.download_end()
+        got.append(outs[(len(scenes) - 1) & 1].tobytes())
+    assert got == want
