@@ -362,6 +362,18 @@ __device__ __forceinline__ int last_le(const uint32_t* a, int count, uint32_t i)
 // boundary tiles of step k have finished, i.e. have finished reading the ghost rows step k+1 overwrites.
 // Boundary tiles come first / last in the grid, so their halo is on the wire while the interior computes.
 // ------------------------------------------------------------------------------------------------
+// Constants of the fp32-offset step kernel (step_float.cuh) and of the neighbour records it reads.
+struct PhysF {
+    float sx, sy;          // fixed-point units -> scaled units (sx a power of two; sy = sx * ky/kx, also one)
+    float zone_shift;      // zone stride * cell width * sx: distance between the even-zone and odd-zone origins
+    float row_shift;       // cell height * sy: distance between the centres of two adjacent cell rows
+    float d0, d1, d2, d3;  // -(n/m) f^(-2(kn-km)) q^fn as a cubic in l = log2(scaled r^2)  (d0 alone if fn == 0)
+    float pair_scale;      // scaled pair sum -> newtons
+    uint32_t zl;           // log2 of the zone stride in cell columns
+    uint32_t half_span;    // (2^zl + 2) cells / 2 in fixed-point units: centre of a zone's used span
+    uint32_t sxbits;       // 32 - LX
+};
+
 struct HaloHeader {     // one per slab, in device memory its two neighbours can reach
     uint32_t flags[2];  // [0]: last epoch published by the lower neighbour, [1]: by the upper one
     uint32_t done[2];   // boundary particles pushed so far in the running step, per side
@@ -372,6 +384,7 @@ struct HaloHeader {     // one per slab, in device memory its two neighbours can
 
 struct HaloArgs {
     uint2* peer_out[2];       // the neighbour's position buffer this step writes ([0] lower, [1] upper); null: none
+    float4* peer_nbr_out[2];  // ... and its neighbour-record buffer (fine grids), or null
     HaloHeader* peer_hdr[2];
     HaloHeader* hdr;
     uint32_t lo_end, hi_start;    // [own_lo, lo_end) goes to the lower neighbour, [hi_start, own_hi) to the upper one
@@ -408,7 +421,25 @@ struct StepArgs {
     Phys ph;
     uint32_t push;  // 1: boundary rows are pushed into the neighbours' ghost rows by this kernel (HaloArgs)
     HaloArgs h;
+    // fine grids: every particle also has a NEIGHBOUR RECORD (x_even, y, x_odd, y): its position as exact scaled fp32
+    // offsets from the centres of its membership cell's even / odd zone and of its membership row (step_float.cuh).
+    // A step reads nbr_in (staged by TMA, no conversion) and writes nbr_out for the next one. Null on coarse grids.
+    const float4* __restrict__ nbr_in;
+    float4* __restrict__ nbr_out;
+    PhysF pf;
 };
+
+// The neighbour record of a particle at `p` whose membership cell is `cell` (local numbering).
+__device__ __forceinline__ float4 nbr_record(uint2 p, uint32_t cell, const Grid& g, const PhysF& pf) {
+    const uint32_t cx = cell & (g.bx - 1);
+    const long long row = (long long)(cell >> g.lx) + g.row_offset;              // global cell row
+    const uint32_t yc = (uint32_t)((2ll * row + 1) << (g.sy - 1));               // centre of that row
+    const uint32_t zq = cx >> pf.zl;
+    const uint32_t xo0 = (((zq & ~1u) << pf.zl) << pf.sxbits) + pf.half_span;    // centre of the even zone's span
+    const float xe = __int2float_rn((int)(p.x - xo0)) * pf.sx;
+    const float y = __int2float_rn((int)(p.y - yc)) * pf.sy;
+    return make_float4(xe, y, xe + ((zq & 1u) ? -pf.zone_shift : pf.zone_shift), y);
+}
 
 // Before a tile that reads a ghost row stages anything: wait for the neighbour's previous step (one thread).
 __device__ __forceinline__ void halo_wait(const StepArgs& a, uint32_t tile) {
@@ -442,16 +473,18 @@ __device__ __forceinline__ void halo_publish_empty(const StepArgs& a) {
 }
 
 // The new position of boundary-row particle i also goes into the neighbour's ghost row.
-__device__ __forceinline__ void halo_push(const StepArgs& a, uint32_t i, uint2 po) {
+__device__ __forceinline__ void halo_push(const StepArgs& a, uint32_t i, uint2 po, float4 nb) {
     const HaloArgs& h = a.h;
     if (h.peer_out[0] && i < h.lo_end) {
         const uint32_t base = ld_acquire_sys(&h.peer_hdr[0]->own_hi);  // the lower slab's upper ghost row
         h.peer_out[0][base + (i - a.own_lo)] = po;
+        if (h.peer_nbr_out[0]) h.peer_nbr_out[0][base + (i - a.own_lo)] = nb;
         __threadfence_system();
         if (atomicAdd(&h.hdr->done[0], 1u) + 1u == h.lo_end - a.own_lo) halo_publish(h, 0);
     }
     if (h.peer_out[1] && i >= h.hi_start) {
         h.peer_out[1][i - h.hi_start] = po;  // the upper slab's lower ghost row starts at 0
+        if (h.peer_nbr_out[1]) h.peer_nbr_out[1][i - h.hi_start] = nb;
         __threadfence_system();
         if (atomicAdd(&h.hdr->done[1], 1u) + 1u == a.own_hi - h.hi_start) halo_publish(h, 1);
     }
@@ -474,7 +507,7 @@ __global__ void halo_publish_kernel(StepArgs a) {
 }
 
 // Cursor + wall force, pair sum, kick + drift and the two stores of one particle (shared by all step kernels).
-__device__ __forceinline__ void finish_particle(uint32_t i, uint2 pi, float2 vi, float sum_x, float sum_y,
+__device__ __forceinline__ void finish_particle(uint32_t i, uint2 pi, float2 vi, uint32_t cell, float sum_x, float sum_y,
                                                 float scale_x, float scale_y, const StepArgs& a) {
     float2 f = field_force(pi, a.ph);
     f.x = fmaf(scale_x, sum_x, f.x);
@@ -484,7 +517,12 @@ __device__ __forceinline__ void finish_particle(uint32_t i, uint2 pi, float2 vi,
     integrate(pi, vi, f, a.ph, po, vo);
     a.pos_out[i] = po;
     a.vel[i] = vo;
-    if (a.push) halo_push(a, i, po);
+    float4 nb = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (a.nbr_out) {
+        nb = nbr_record(po, cell, a.g, a.pf);
+        a.nbr_out[i] = nb;
+    }
+    if (a.push) halo_push(a, i, po, nb);
 }
 
 template <int KN, int FRAC, bool ANISO, bool CG>
@@ -505,7 +543,7 @@ __device__ __forceinline__ void step_particle(uint32_t i, uint2 pi, float2 vi, u
         if (d == 1) window_accumulate<KN, FRAC, ANISO, true, CG>(win, (int)(e - s), pi, a.ph, gx, gy);  // contains i
         else window_accumulate<KN, FRAC, ANISO, false, CG>(win, (int)(e - s), pi, a.ph, gx, gy);
     }
-    finish_particle(i, pi, vi, gx.x + gx.y, gy.x + gy.y, a.ph.pair_scale, a.ph.pair_scale_y, a);
+    finish_particle(i, pi, vi, cell, gx.x + gx.y, gy.x + gy.y, a.ph.pair_scale, a.ph.pair_scale_y, a);
 }
 
 template <int KN, int FRAC, bool ANISO>
@@ -589,7 +627,7 @@ __global__ void __launch_bounds__(kTile) allpairs_step_kernel(const StepArgs a) 
             pair2<KN, FRAC, ANISO, false, true, true>(pi, s_pos[k], s_pos[k + 1], a.ph, gx, gy);
         if (k < count) pair2<KN, FRAC, ANISO, true, true, true>(pi, s_pos[k], pi, a.ph, gx, gy);
     }
-    if (live) finish_particle(i, pi, a.vel[i], gx.x + gx.y, gy.x + gy.y, a.ph.pair_scale, a.ph.pair_scale_y, a);
+    if (live) finish_particle(i, pi, a.vel[i], 0u, gx.x + gx.y, gy.x + gy.y, a.ph.pair_scale, a.ph.pair_scale_y, a);
 }
 
 // CompactArray ingest: wire-format records (already free of nulls) -> the structure of arrays, input order kept.
@@ -788,7 +826,8 @@ __global__ void scatter_kernel(Source src, Grid g, const uint32_t* __restrict__ 
 __global__ void gather_kernel(Source src, uint32_t p_lo, uint32_t p_hi, Grid g,
                               const uint32_t* __restrict__ cell_start, const uint32_t* __restrict__ perm,
                               uint2* __restrict__ pos_out, float2* __restrict__ vel_out,
-                              int32_t* __restrict__ ty_out, uint32_t* __restrict__ cell_id_out) {
+                              int32_t* __restrict__ ty_out, uint32_t* __restrict__ cell_id_out,
+                              float4* __restrict__ nbr_out, PhysF pf) {
     uint32_t p = p_lo + blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= p_hi) return;
     uint32_t c = perm[p];
@@ -806,6 +845,16 @@ __global__ void gather_kernel(Source src, uint32_t p_lo, uint32_t p_hi, Grid g,
     vel_out[dst] = vel;
     ty_out[dst] = ty;
     cell_id_out[dst] = key;
+    if (nbr_out) nbr_out[dst] = nbr_record(pos, key, g, pf);
+}
+
+// Neighbour records of particles [lo, hi) from their positions and membership cells (found in cell_start): ghost
+// rows that arrived as bare positions, or everything after the metadata changed the scale.
+__global__ void nbr_rebuild_kernel(const uint2* __restrict__ pos, const uint32_t* __restrict__ cell_start, Grid g,
+                                   PhysF pf, uint32_t lo, uint32_t hi, float4* __restrict__ nbr) {
+    const uint32_t i = lo + blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= hi) return;
+    nbr[i] = nbr_record(pos[i], (uint32_t)last_le(cell_start, (int)g.cells, i), g, pf);
 }
 
 // The few numbers the host needs after a binning: where the owned rows and their two boundary rows
@@ -1044,6 +1093,8 @@ struct PsimStepper {
     float2* vel[2] = {nullptr, nullptr};
     int32_t* ty[2] = {nullptr, nullptr};
     int cur_pos = 0, cur_vel = 0, cur_ty = 0;
+    float4* nbr[2] = {nullptr, nullptr};  // neighbour records (fine grids), same ping-pong index as pos
+    bool nbr_stale = true;                // nbr[cur_pos] does not match pos[cur_pos] / the current scale
     uint32_t* cell_id = nullptr;
     TileDesc* tiles = nullptr;
     uint32_t* cell_start = nullptr;  // cells + 1 (+ padding)
@@ -1052,7 +1103,6 @@ struct PsimStepper {
     uint32_t* tile_base = nullptr;   // own_rows + 1: first tile of every owned row
     uint32_t* d_couple_tiles = nullptr;
     TileC* tiles_c = nullptr;
-    uint32_t* col_start = nullptr;   // tiles_c_cap x kColStride: band slot of every column of every tile
     uint32_t tiles_c_cap = 0, n_tiles_c = 0;
     bool float_grid = false;         // the grid is fine enough for step_kernel_c's exact fp32 offsets
     bool float_path = false;         // ... and the metadata's physics has a step_kernel_c variant
@@ -1083,8 +1133,9 @@ struct PsimStepper {
     // halo push (HaloArgs): this slab's header, the neighbours' buffers and headers as this device sees them
     HaloHeader* hdr = nullptr;
     uint2* peer_pos[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};  // [side][buffer]
+    float4* peer_nbr[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};
     HaloHeader* peer_hdr[2] = {nullptr, nullptr};
-    void* ipc_mapped[2][3] = {{nullptr, nullptr, nullptr}, {nullptr, nullptr, nullptr}};  // to close at destroy
+    void* ipc_mapped[2][5] = {};  // to close at destroy: pos[0], pos[1], header, nbr[0], nbr[1]
     bool push = false;           // steps push their boundary rows (else: exchange after every step)
     bool ghosts_by_push = false; // the ghost rows the next step reads are being written by the neighbours' last step
     uint32_t halo_epoch = 0;     // epoch the last step published
@@ -1301,6 +1352,7 @@ bool make_phys_f(const FrameMetadata& m, const Phys& ph, const Grid& g, int kn, 
     const uint32_t stride = 1u << pf.zl;
     pf.half_span = (stride + 2u) << (g.sx - 1);
     pf.zone_shift = (float)std::ldexp((double)stride, (int)g.sx + ex);
+    pf.row_shift = (float)(std::ldexp(1.0, (int)g.sy) * (double)pf.sy);
     // scaled r^2 = true (r/sigma)^2 / f^2, so with qs = 1/scaled r^2 = q f^2:
     //   g f^(2 km) = qs^km - (n/m) f^(-2(kn-km)) qs^kn q^fn ,   q^fn = 2^z,  z = fn log2 q = -fn (l + 2 log2 f)
     const double km = ph.km, knd = ph.kn, fn = ph.fn;
@@ -1325,6 +1377,7 @@ void apply_metadata(PsimStepper* s, const FrameMetadata& m) {
     s->phys = make_phys(m, &s->kernel_kn, &s->kernel_frac, &s->kernel_aniso);
     s->float_path = s->float_grid && !s->force_int_path &&
                     make_phys_f(m, s->phys, s->grid, s->kernel_kn, s->kernel_frac, &s->physf);
+    s->nbr_stale = true;  // the records carry the old scale (or were not kept at all): rebuilt before the next step
 }
 
 template <int KN, int FRAC>
@@ -1347,8 +1400,6 @@ void launch_step_c(PsimStepper* s, const StepArgs& a) {
     StepArgsC ac;
     ac.couple_i0 = s->couple_i0;
     ac.tiles = s->tiles_c;
-    ac.col_start = s->col_start;
-    ac.pf = s->physf;
     if (s->kernel_frac == kFracNone) step_kernel_c<KN, kFracNone><<<s->n_tiles_c, kCouples, 0, s->stream>>>(a, ac);
     else step_kernel_c<KN, kFracPoly><<<s->n_tiles_c, kCouples, 0, s->stream>>>(a, ac);
 }
@@ -1512,6 +1563,24 @@ XferOp ghost_positions_op(PsimStepper* s) {
     return op;
 }
 
+// Neighbour records of [lo, hi) of the current buffers from the positions there (nbr_rebuild_kernel).
+int enqueue_nbr_rebuild(PsimStepper* s, uint32_t lo, uint32_t hi) {
+    if (hi <= lo) return PSIM_OK;
+    nbr_rebuild_kernel<<<div_up(hi - lo, 256), 256, 0, s->stream>>>(s->pos[s->cur_pos], s->cell_start, s->grid, s->physf,
+                                                                   lo, hi, s->nbr[s->cur_pos]);
+    s->launches += 1;
+    CK(cudaGetLastError());
+    return PSIM_OK;
+}
+
+// The ghost rows have just arrived as bare positions (an exchange): give them their neighbour records.
+int refresh_ghost_records(PsimStepper* s) {
+    if (!s->float_path || s->nranks == 1) return PSIM_OK;
+    int rc = enqueue_nbr_rebuild(s, 0, s->own_lo);
+    if (rc) return rc;
+    return enqueue_nbr_rebuild(s, s->own_hi, s->n_total);
+}
+
 // ------------------------------------------------------------------------------------------------
 // Binning, phase by phase (every phase is run for all slabs of the team before the next one starts)
 // ------------------------------------------------------------------------------------------------
@@ -1653,7 +1722,8 @@ int bin_phase_place(PsimStepper* s, bool ingest, XferOp& op) {
     if (s->n) {
         scatter_kernel<<<div_up(cand, tb), tb, 0, s->stream>>>(src, s->grid, s->cell_start, s->rank_in_cell, s->perm);
         gather_kernel<<<div_up(s->n, tb), tb, 0, s->stream>>>(src, s->own_lo, s->own_hi, s->grid, s->cell_start,
-                                                              s->perm, s->pos[np], s->vel[nv], s->ty[nt], s->cell_id);
+                                                              s->perm, s->pos[np], s->vel[nv], s->ty[nt], s->cell_id,
+                                                              s->float_path ? s->nbr[np] : nullptr, s->physf);
         s->launches += 2;
         CK(cudaGetLastError());
     }
@@ -1671,9 +1741,8 @@ int bin_phase_tiles(PsimStepper* s) {
     tile_desc_kernel<<<div_up(tiles, 128), 128, 0, s->stream>>>(s->cell_start, s->grid, s->own_lo, s->own_hi, s->tiles);
     s->launches += 1;
     if (s->float_grid && s->n_tiles_c) {
-        tile_build_kernel<<<div_up(s->n_tiles_c, 4), 128, 0, s->stream>>>(s->cell_start, s->pad_start, s->tile_base,
-                                                                          s->couple_i0, s->cell_id, s->grid, s->tiles_c,
-                                                                          s->col_start);
+        tile_build_kernel<<<div_up(s->n_tiles_c, 128), 128, 0, s->stream>>>(s->cell_start, s->pad_start, s->tile_base,
+                                                                          s->couple_i0, s->cell_id, s->grid, s->tiles_c);
         s->launches += 1;
     }
     CK(cudaGetLastError());
@@ -1742,6 +1811,9 @@ int team_bin(const Team& t, bool ingest, const Particle* records, uint32_t count
         if ((rc = bin_phase_place(t.ranks[r], ingest, ops[r]))) return rc;
     if ((rc = team_exchange(t, ops))) return rc;
     for (int r = 0; r < t.count; ++r) {
+        PsimStepper* s = t.ranks[r];
+        if ((rc = refresh_ghost_records(s))) return rc;
+        s->nbr_stale = !s->float_path;  // the gather wrote the owned rows' records, the line above the ghosts'
         if ((rc = bin_phase_tiles(t.ranks[r]))) return rc;
         if (!ingest) t.ranks[r]->rebins_executed += 1;
     }
@@ -1764,6 +1836,17 @@ int enqueue_step(PsimStepper* s) {
     a.own_hi = s->own_hi;
     a.g = s->grid;
     a.ph = s->phys;
+    a.pf = s->physf;
+    a.nbr_in = a.nbr_out = nullptr;
+    if (s->float_path && !s->compact_mode) {
+        if (s->nbr_stale) {  // new scale (metadata) or records not kept so far: rebuild them from the positions
+            int rc = enqueue_nbr_rebuild(s, 0, s->n_total);
+            if (rc) return rc;
+            s->nbr_stale = false;
+        }
+        a.nbr_in = s->nbr[s->cur_pos];
+        a.nbr_out = s->nbr[s->cur_pos ^ 1];
+    }
     a.push = s->push ? 1u : 0u;
     std::memset(&a.h, 0, sizeof a.h);
     if (s->push) {
@@ -1772,6 +1855,7 @@ int enqueue_step(PsimStepper* s) {
         h.hdr = s->hdr;
         for (int side = 0; side < 2; ++side) {
             h.peer_out[side] = s->peer_pos[side][out];
+            h.peer_nbr_out[side] = a.nbr_out ? s->peer_nbr[side][out] : nullptr;
             h.peer_hdr[side] = s->peer_hdr[side];
             h.wait_epoch[side] = s->ghosts_by_push ? s->halo_epoch : 0u;
         }
@@ -1833,7 +1917,10 @@ int team_step(const Team& t) {
     if (t.ranks[0]->nranks == 1 || t.ranks[0]->push) return PSIM_OK;  // pushed by the step kernel itself
     std::vector<XferOp> ops(t.count);
     for (int r = 0; r < t.count; ++r) ops[r] = ghost_positions_op(t.ranks[r]);
-    return team_exchange(t, ops);
+    if ((rc = team_exchange(t, ops))) return rc;
+    for (int r = 0; r < t.count; ++r)
+        if ((rc = refresh_ghost_records(t.ranks[r]))) return rc;
+    return PSIM_OK;
 }
 
 int enqueue_snapshot(PsimStepper* s) {
@@ -2021,6 +2108,7 @@ void psim_destroy(PsimStepper* s) {
     }
     for (int k = 0; k < 2; ++k) {
         cudaFree(s->pos[k]);
+        cudaFree(s->nbr[k]);
         cudaFree(s->vel[k]);
         cudaFree(s->ty[k]);
         cudaFree(s->outbox[k]);
@@ -2033,7 +2121,6 @@ void psim_destroy(PsimStepper* s) {
     cudaFree(s->tile_base);
     cudaFree(s->d_couple_tiles);
     cudaFree(s->tiles_c);
-    cudaFree(s->col_start);
     cudaFree(s->cell_count);
     cudaFree(s->block_sum);
     cudaFree(s->rank_in_cell);
@@ -2170,7 +2257,10 @@ int psim_create(const PsimConfig* config, PsimStepper** out) {
         CKC(cudaMalloc(&st->tile_base, sizeof(uint32_t) * ((size_t)g.own_rows + 1)));
         CKC(cudaMalloc(&st->d_couple_tiles, sizeof(uint32_t)));
         CKC(cudaMalloc(&st->tiles_c, sizeof(TileC) * (size_t)st->tiles_c_cap));
-        CKC(cudaMalloc(&st->col_start, sizeof(uint32_t) * kColStride * (size_t)st->tiles_c_cap));
+        for (int k = 0; k < 2; ++k) {
+            CKC(cudaMalloc(&st->nbr[k], sizeof(float4) * (cap_total + kPadParticles)));
+            CKC(cudaMemset(st->nbr[k], 0, sizeof(float4) * (cap_total + kPadParticles)));
+        }
     }
     CKC(cudaMalloc(&st->cell_count, sizeof(uint32_t) * (size_t)g.cells));
     CKC(cudaMalloc(&st->block_sum, sizeof(uint32_t) * (size_t)div_up(g.cells, kScanBlock)));
@@ -2220,8 +2310,10 @@ int psim_comm_unique_id(void* out128) {
 struct HaloExport {
     cudaIpcMemHandle_t pos[2];
     cudaIpcMemHandle_t hdr;
+    cudaIpcMemHandle_t nbr[2];  // fine grids only
     uint32_t valid;
-    uint32_t _pad[3];
+    uint32_t has_nbr;
+    uint32_t _pad[2];
 };
 
 // Map the neighbours' buffers (one process per slab). Collective over the communicator. Any failure on any
@@ -2235,6 +2327,11 @@ int connect_peers(PsimStepper* s) {
         ok = cudaIpcGetMemHandle(&mine.pos[0], s->pos[0]) == cudaSuccess &&
              cudaIpcGetMemHandle(&mine.pos[1], s->pos[1]) == cudaSuccess &&
              cudaIpcGetMemHandle(&mine.hdr, s->hdr) == cudaSuccess;
+        if (ok && s->nbr[0]) {
+            ok = cudaIpcGetMemHandle(&mine.nbr[0], s->nbr[0]) == cudaSuccess &&
+                 cudaIpcGetMemHandle(&mine.nbr[1], s->nbr[1]) == cudaSuccess;
+            mine.has_nbr = 1;
+        }
         cudaGetLastError();
     }
     mine.valid = ok ? 1u : 0u;
@@ -2263,8 +2360,8 @@ int connect_peers(PsimStepper* s) {
             ok = 0;
             break;
         }
-        const cudaIpcMemHandle_t* handles[3] = {&e.pos[0], &e.pos[1], &e.hdr};
-        for (int k = 0; k < 3 && ok; ++k) {
+        const cudaIpcMemHandle_t* handles[5] = {&e.pos[0], &e.pos[1], &e.hdr, &e.nbr[0], &e.nbr[1]};
+        for (int k = 0; k < (e.has_nbr ? 5 : 3) && ok; ++k) {
             void* p = nullptr;
             if (cudaIpcOpenMemHandle(&p, *handles[k], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
                 cudaGetLastError();
@@ -2287,6 +2384,8 @@ int connect_peers(PsimStepper* s) {
             s->peer_pos[side][0] = static_cast<uint2*>(s->ipc_mapped[side][0]);
             s->peer_pos[side][1] = static_cast<uint2*>(s->ipc_mapped[side][1]);
             s->peer_hdr[side] = static_cast<HaloHeader*>(s->ipc_mapped[side][2]);
+            s->peer_nbr[side][0] = static_cast<float4*>(s->ipc_mapped[side][3]);
+            s->peer_nbr[side][1] = static_cast<float4*>(s->ipc_mapped[side][4]);
         }
     }
     return PSIM_OK;
@@ -2620,7 +2719,8 @@ int psim_tile_stats(PsimStepper* s, PsimTileStats* out) {
         for (const TileC& x : t) {
             out->tiles_staged += x.fits ? 1u : 0u;
             out->threads_live += x.nk;
-            out->max_columns = std::max(out->max_columns, x.ncol);
+            out->max_columns = std::max(out->max_columns, x.cs_cnt[1]);
+            for (int d = 0; d < 3; ++d) out->max_row_particles = std::max(out->max_row_particles, x.p_cnt[d]);
         }
         out->threads_launched = (uint64_t)s->n_tiles_c * kCouples;
     } else {
@@ -2699,6 +2799,8 @@ int psim_group_create(PsimStepper* const* steppers, uint32_t count, PsimGroup** 
             const bool has = m->push && peer >= 0 && peer < (int)count;
             m->peer_pos[side][0] = has ? g->ranks[peer]->pos[0] : nullptr;
             m->peer_pos[side][1] = has ? g->ranks[peer]->pos[1] : nullptr;
+            m->peer_nbr[side][0] = has ? g->ranks[peer]->nbr[0] : nullptr;
+            m->peer_nbr[side][1] = has ? g->ranks[peer]->nbr[1] : nullptr;
             m->peer_hdr[side] = has ? g->ranks[peer]->hdr : nullptr;
         }
     }
@@ -2715,6 +2817,7 @@ void psim_group_destroy(PsimGroup* g) {
         m->push = false;
         for (int side = 0; side < 2; ++side) {
             m->peer_pos[side][0] = m->peer_pos[side][1] = nullptr;
+            m->peer_nbr[side][0] = m->peer_nbr[side][1] = nullptr;
             m->peer_hdr[side] = nullptr;
         }
     }
