@@ -49,7 +49,7 @@ struct __align__(16) TileC {
 static_assert(sizeof(TileC) == 64, "TileC is read as four 16-byte words");
 
 struct StepArgsC {
-    const uint32_t* __restrict__ couple_i0;  // per couple: index of its first particle | (has a second one) << 31
+    const uint2* __restrict__ couple_i0;  // per couple: (index of its first particle | (has a second one) << 31, its cell)
     const TileC* __restrict__ tiles;
 };
 
@@ -110,7 +110,7 @@ __global__ void __launch_bounds__(kCouples, 9) step_kernel_c(const StepArgs a, c
     }
     if (!t.fits) {  // very sparse or very crowded spot: same physics straight from global memory, one particle at a time
         if (!live) return;
-        const uint32_t w = ac.couple_i0[t.k0 + threadIdx.x];
+        const uint32_t w = ac.couple_i0[t.k0 + threadIdx.x].x;
         const uint32_t i0 = w & 0x7FFFFFFFu;
         const uint32_t* cs[3] = {a.cell_start, a.cell_start, a.cell_start};
         const uint2* pp[3] = {a.pos_in, a.pos_in, a.pos_in};
@@ -135,30 +135,31 @@ __global__ void __launch_bounds__(kCouples, 9) step_kernel_c(const StepArgs a, c
         }
     }
 
-    // this thread's couple (the loads fly while the stencil arrives)
-    uint32_t i0 = a.own_lo, has1 = 0;
+    // this thread's couple
+    uint32_t i0 = a.own_lo, has1 = 0, cell = t.row << g.lx;
     if (live) {
-        const uint32_t w = ac.couple_i0[t.k0 + threadIdx.x];
-        i0 = w & 0x7FFFFFFFu;
-        has1 = w >> 31;
+        const uint2 w = ac.couple_i0[t.k0 + threadIdx.x];
+        i0 = w.x & 0x7FFFFFFFu;
+        has1 = w.x >> 31;
+        cell = w.y;
     }
     const uint32_t i1 = i0 + has1;  // a half-empty couple computes its only particle twice
+    // positions and velocities are needed by the epilogue only: these loads fly during the pair loops
     const uint2 p0 = a.pos_in[i0], p1 = a.pos_in[i1];
     const float2 v0 = a.vel[i0], v1 = a.vel[i1];
-    const uint32_t cell = a.cell_id[i0];
     const uint32_t cx = cell & (g.bx - 1);
     const uint32_t x0c = cx == 0 ? 0 : cx - 1, x1c = cx == g.bx - 1 ? cx : cx + 1;
-
-    // own offsets: x from the centre of the thread's zone, y from the centre of the tile's row
-    const uint32_t zt = x0c >> pf.zl;
-    const uint32_t xo = ((zt << pf.zl) << pf.sxbits) + pf.half_span;
-    const uint32_t yc = (uint32_t)((2ll * ((long long)t.row + g.row_offset) + 1) << (g.sy - 1));
-    const float2 nx = make_float2(-(__int2float_rn((int)(p0.x - xo)) * pf.sx), -(__int2float_rn((int)(p1.x - xo)) * pf.sx));
-    const float2 ny0 = make_float2(-(__int2float_rn((int)(p0.y - yc)) * pf.sy), -(__int2float_rn((int)(p1.y - yc)) * pf.sy));
+    const uint32_t par = (x0c >> pf.zl) & 1u;  // parity of the thread's zone: which x offset of a record it reads
 
     __syncthreads();  // the barrier is initialised before anyone polls it
     mbar_wait(&s_bar, 0);
     if (!live) return;
+
+    // own offsets: the thread's two particles are records of the own row too (x of the same parity: their cell is
+    // one of the thread's stencil columns)
+    const float2* own = reinterpret_cast<const float2*>(s_nb[1]) + par;
+    const float2 o0 = own[2 * (i0 - t.p_lo[1])], o1 = own[2 * (i1 - t.p_lo[1])];
+    const float2 nx = make_float2(-o0.x, -o1.x), ny0 = make_float2(-o0.y, -o1.y);
 
     float2 gx = splat(0.f), gy = splat(0.f);
 #pragma unroll
@@ -169,9 +170,10 @@ __global__ void __launch_bounds__(kCouples, 9) step_kernel_c(const StepArgs a, c
         // a neighbour in the row below / above sits one row distance further down / up than its own-row offset says
         const float2 ny = __fadd2_rn(ny0, splat((float)(d - 1) * pf.row_shift));
         // (x_even, y) or (x_odd, y): the 8 bytes at offset 0 or 8 of a record
-        const float2* nb = reinterpret_cast<const float2*>(s_nb[d]) + (zt & 1u);
-        for (uint32_t k = ws; k < we; ++k) {
-            const float2 j = nb[2 * k];
+        const float4* nb = s_nb[d] + ws;
+        const float4* const nb_end = s_nb[d] + we;
+        for (; nb < nb_end; ++nb) {
+            const float2 j = reinterpret_cast<const float2*>(nb)[par];
             if (d == 1) pairc<KN, FRAC, true>(j.x, j.y, nx, ny, pf, gx, gy);
             else pairc<KN, FRAC, false>(j.x, j.y, nx, ny, pf, gx, gy);
         }
@@ -182,14 +184,15 @@ __global__ void __launch_bounds__(kCouples, 9) step_kernel_c(const StepArgs a, c
 
 // ---- re-bin side of the couples ------------------------------------------------------------------------
 
-// couple_i0[k] for the couples of every cell; couples are numbered by pad_start / 2.
+// couple_i0[k] for the couples of every cell (the cell is the one of this binning, i.e. the membership cell of the
+// particles until the next one); couples are numbered by pad_start / 2.
 __global__ void couple_build_kernel(const uint32_t* __restrict__ cell_start, const uint32_t* __restrict__ pad_start,
-                                    uint32_t cells, uint32_t* __restrict__ couple_i0) {
+                                    uint32_t cells, uint2* __restrict__ couple_i0) {
     uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= cells) return;
     const uint32_t s = cell_start[c], n = cell_start[c + 1] - s;
     uint32_t k = pad_start[c] >> 1;
-    for (uint32_t m = 0; m < n; m += 2, ++k) couple_i0[k] = (s + m) | (m + 1 < n ? 0x80000000u : 0u);
+    for (uint32_t m = 0; m < n; m += 2, ++k) couple_i0[k] = make_uint2((s + m) | (m + 1 < n ? 0x80000000u : 0u), c);
 }
 
 // Tiles of every owned row: ceil(couples of the row / kCouples); single block: exclusive scan into
@@ -238,8 +241,8 @@ __global__ void __launch_bounds__(1024) row_tiles_kernel(const uint32_t* __restr
 
 // One TileC per tile index b in [0, tile_base[own_rows]).
 __global__ void tile_build_kernel(const uint32_t* __restrict__ cell_start, const uint32_t* __restrict__ pad_start,
-                                  const uint32_t* __restrict__ tile_base, const uint32_t* __restrict__ couple_i0,
-                                  const uint32_t* __restrict__ cell_id, Grid g, TileC* __restrict__ tiles) {
+                                  const uint32_t* __restrict__ tile_base, const uint2* __restrict__ couple_i0,
+                                  Grid g, TileC* __restrict__ tiles) {
     const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= tile_base[g.own_rows]) return;
     // the last row whose base is <= b (rows without tiles share their successor's base and are skipped over)
@@ -250,8 +253,8 @@ __global__ void tile_build_kernel(const uint32_t* __restrict__ cell_start, const
     t.k0 = row_k0 + (b - tile_base[r]) * kCouples;
     t.nk = min(row_k1 - t.k0, (uint32_t)kCouples);
     t.row = row;
-    const uint32_t c_first = cell_id[couple_i0[t.k0] & 0x7FFFFFFFu] & (g.bx - 1);
-    const uint32_t c_last = cell_id[couple_i0[t.k0 + t.nk - 1] & 0x7FFFFFFFu] & (g.bx - 1);
+    const uint32_t c_first = couple_i0[t.k0].y & (g.bx - 1);
+    const uint32_t c_last = couple_i0[t.k0 + t.nk - 1].y & (g.bx - 1);
     const uint32_t col_lo = c_first == 0 ? 0 : c_first - 1;
     const uint32_t col_hi = c_last == g.bx - 1 ? c_last : c_last + 1;
     bool fits = col_hi - col_lo + 1 <= (uint32_t)kColCap;

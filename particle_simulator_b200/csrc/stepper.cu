@@ -1099,7 +1099,7 @@ struct PsimStepper {
     TileDesc* tiles = nullptr;
     uint32_t* cell_start = nullptr;  // cells + 1 (+ padding)
     uint32_t* pad_start = nullptr;   // cells + 1: prefix sum of the cell counts rounded up to even (step_float.cuh)
-    uint32_t* couple_i0 = nullptr;   // per couple: first particle | has-a-second << 31
+    uint2* couple_i0 = nullptr;      // per couple: (first particle | has-a-second << 31, cell)
     uint32_t* tile_base = nullptr;   // own_rows + 1: first tile of every owned row
     uint32_t* d_couple_tiles = nullptr;
     TileC* tiles_c = nullptr;
@@ -1742,7 +1742,7 @@ int bin_phase_tiles(PsimStepper* s) {
     s->launches += 1;
     if (s->float_grid && s->n_tiles_c) {
         tile_build_kernel<<<div_up(s->n_tiles_c, 128), 128, 0, s->stream>>>(s->cell_start, s->pad_start, s->tile_base,
-                                                                          s->couple_i0, s->cell_id, s->grid, s->tiles_c);
+                                                                          s->couple_i0, s->grid, s->tiles_c);
         s->launches += 1;
     }
     CK(cudaGetLastError());
@@ -2253,7 +2253,7 @@ int psim_create(const PsimConfig* config, PsimStepper** out) {
         st->tiles_c_cap = (uint32_t)((cap + std::min<size_t>(cap, (size_t)g.own_rows * g.bx)) / 2 / kCouples + g.own_rows + 1);
         CKC(cudaMalloc(&st->pad_start, sizeof(uint32_t) * ((size_t)g.cells + 1 + kPadCells)));
         CKC(cudaMemset(st->pad_start, 0, sizeof(uint32_t) * ((size_t)g.cells + 1 + kPadCells)));
-        CKC(cudaMalloc(&st->couple_i0, sizeof(uint32_t) * couples));
+        CKC(cudaMalloc(&st->couple_i0, sizeof(uint2) * couples));
         CKC(cudaMalloc(&st->tile_base, sizeof(uint32_t) * ((size_t)g.own_rows + 1)));
         CKC(cudaMalloc(&st->d_couple_tiles, sizeof(uint32_t)));
         CKC(cudaMalloc(&st->tiles_c, sizeof(TileC) * (size_t)st->tiles_c_cap));
