@@ -2597,6 +2597,12 @@ int psim_sync(PsimStepper* s) {
     if (!s) return PSIM_EINVAL;
     CK(cudaSetDevice(s->device));
     CK(cudaStreamSynchronize(s->stream));
+    if (s->push && s->hdr) {  // a step that gave up waiting for a neighbour's halo says so here
+        uint32_t halo_error = 0;
+        CK(cudaMemcpy(&halo_error, &s->hdr->error, sizeof halo_error, cudaMemcpyDeviceToHost));
+        if (halo_error)
+            return fail(s, PSIM_ECUDA, "slab %d: a step waited 20 s for a neighbour's halo (did a neighbour rank die?)", s->rank);
+    }
     if (s->timing) return collect_timing(s);
     return PSIM_OK;
 }

@@ -1,0 +1,40 @@
+"""The synthetic workloads of BASELINE.json as frames (host side only)."""
+import numpy as np
+
+from particle_simulator_b200 import workloads
+from particle_simulator_b200.slabs import slab_of
+
+
+def test_clustered_mixed_scene_is_lopsided_and_reproducible():
+    w = workloads.clustered_mixed((10, 10), clusters=4, side=60, gas=2000, seed=5)
+    p = w.frame.particles
+    assert w.particles == 4 * 60 * 60 + 2000 and len(p) == w.particles
+    assert set(np.unique(p["ty"])) == {0, 1}
+    assert float(w.frame.metadata["step_dt"]) == np.float32(10e-15)
+    owner = slab_of(p["y"], 8, 10)
+    held = np.bincount(owner, minlength=8)
+    assert held.max() > 2 * held.mean()  # a row decomposition of it is badly balanced
+    again = workloads.clustered_mixed((10, 10), clusters=4, side=60, gas=2000, seed=5)
+    assert again.frame.tobytes() == w.frame.tobytes()
+    other = workloads.clustered_mixed((10, 10), clusters=4, side=60, gas=2000, seed=6)
+    assert other.frame.tobytes() != w.frame.tobytes()
+
+
+def test_heat_scales_velocities_only():
+    w = workloads.lattice(20, 20, (6, 6), 1.0, 1.0, 10.0, seed=2)
+    before = w.frame.particles.copy()
+    workloads.heat(w.frame, 1.5)
+    after = w.frame.particles
+    assert np.array_equal(after["x"], before["x"]) and np.array_equal(after["ty"], before["ty"])
+    assert np.allclose(after["vx"], 1.5 * before["vx"]) and np.allclose(after["vy"], 1.5 * before["vy"])
+
+
+def test_slab_crystal_rows_partition_the_crystal():
+    geo = workloads.slab_crystal_geometry(4, per_slab=40000, rows_per_slab_log2=6, grid_x_log2=8)
+    parts = [workloads.slab_crystal(r, 4, per_slab=40000, rows_per_slab_log2=6, grid_x_log2=8) for r in range(4)]
+    ly = geo["grid_log2"][1]
+    owned = 0
+    for r, w in enumerate(parts):
+        p = w.frame.particles
+        owned += int((slab_of(p["y"], 4, ly) == r).sum())  # each rank is handed a little more than its own rows
+    assert owned == geo["nx"] * geo["ny"]
