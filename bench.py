@@ -184,6 +184,35 @@ def cpu_baseline(wl, budget_steps: int) -> dict:
                       f"Device::CpuThreadPool ({t:.1f} s)"}
 
 
+def reference_cuda_baseline(wl, budget_steps: int) -> dict:
+    """The reference's EXISTING CUDA backend (bucket_step_gpu / bucket_move_gpu, kernel_bucket.cuh:96-110, compiled
+    for sm_100a into oracle/_ref -- its own build ships sm_86 / sm_89 SASS only) on the same B200 and the same scene:
+    Device::Gpu, gpu_threads_per_block_log2 = 7, Kernel::run_async + sync timed (no copies). A reported baseline."""
+    from oracle.oracle import RefOracle, ref_available
+    from particle_simulator_b200.frame import DEVICE_GPU
+
+    lx, ly = wl.grid_log2
+    if not ref_available(lx, ly):
+        return {"value": None, "unit": "particle-updates/s", "kind": "reference-cuda",
+                "sample": f"oracle/_ref/libref_{lx}_{ly}.so not built"}
+    ref = RefOracle(lx, ly)
+    if ref.gpu_count == 0:
+        return {"value": None, "unit": "particle-updates/s", "kind": "reference-cuda", "sample": "the reference found no GPU"}
+    fb = wl.frame.copy()
+    fb.metadata["device"] = DEVICE_GPU
+    fb.metadata["steps_per_frame"] = budget_steps
+    used = ref.prepare(fb)
+    executed = schedule_steps(budget_steps)
+    ref.run_frame()  # warm-up
+    frames = 2
+    t = sum(ref.run_frame() for _ in range(frames))
+    return {"value": wl.particles * executed * frames / t, "unit": "particle-updates/s", "kind": "reference-cuda",
+            "ms_per_leapfrog_step": 1e3 * t / (frames * executed),
+            "sample": f"{frames} frames of {executed} leapfrog steps on the full {wl.particles}-particle scene, the "
+                      f"reference's bucket_step_gpu / bucket_move_gpu rebuilt for sm_100a, device field {used}, "
+                      f"{ref.slot_count} slots of {ref.capacity} per cell ({t:.2f} s)"}
+
+
 def run_ours(args, rank: int, world: int, local_rank: int) -> None:
     import torch
     import torch.distributed as dist
@@ -344,7 +373,9 @@ def run_ours(args, rank: int, world: int, local_rank: int) -> None:
             "clocks": clocks,
         }
         if world == 1 and not args.no_cpu_baseline:
+            st.close()  # the reference allocates its own slot arrays on this GPU
             line["cpu_baseline"] = cpu_baseline(wl, args.cpu_steps)
+            line["reference_cuda_baseline"] = reference_cuda_baseline(wl, args.cpu_steps)
         print(json.dumps(line))
     st.close()
     if world > 1:
