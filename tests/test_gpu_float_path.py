@@ -4,7 +4,7 @@ axis) run, which stages stencil neighbours as exact fp32 offsets from zone / til
 Checked (1) against the oracle restatement of the reference's bucket_step_kernel (kernel_bucket.cuh:40-94) on a
 1024 x 1024 grid, and (2) against this library's integer-separation kernel (the one coarse grids run, forced
 with PSIM_FORCE_INT_PATH=1) on scenes built to hit the fp32 path's corner cases: zone seams, the first and
-last cell columns and rows, tiles that straddle rows, sparse tiles that fall back to global memory, crowded
+last cell columns and rows, sparse tiles that fall back to global memory, crowded
 cells, drifted (stale-membership) particles, walls, a 2:1 box on an 8192 x 4096 grid.
 The two kernels compute the same separations exactly and differ only in rounding of the force law, so they
 must agree to the L2 tolerance of test_gpu_parity (1e-5 of the largest pair force).
@@ -198,3 +198,45 @@ def test_walls_and_cursor_on_fine_grid():
     fb = boxed(100 * 100, grid, meta)
     io.scene_hex_square(fb, 100, 100, (100 * 2.05e-10 + 6e-10, 100 * 1.8e-10 + 6e-10), 1.0, 1.0, 30.0, 0, seed=27)
     assert_paths_agree(fb, grid, what="walls")
+
+
+def test_metadata_updates_between_steps_rebuild_the_neighbour_records():
+    """The records carry the scale of sigma and exist only while the physics has an fp32 variant: a header-only
+    metadata update (Kernel::write_metadata, kernel.cuh:96-101) changes sigma, then switches to exponents that run
+    the integer kernel, then back. Same sequence on the integer kernel throughout; states must track each other."""
+    from particle_simulator_b200.stepper import Stepper
+
+    grid = (10, 10)
+    fb = boxed(160 * 160, grid)
+    w = float(fb.metadata["box_width"])
+    io.scene_hex_square(fb, 160, 160, (0.4 * w, 0.55 * w), 1.04, 20.0, 60.0, 0, seed=28)
+    metas = [fb.metadata.copy() for _ in range(4)]
+    metas[1]["particles"][0]["sigma"] = np.float32(3.7e-10)        # another scale: (kx / sigma) changes
+    metas[2]["particles"][0]["n"] = np.float32(24.0)               # no fp32 variant: step_kernel takes over
+    metas[3]["particles"][0]["n"] = np.float32(12.0)               # back, with other powers
+
+    def run(force_int: bool):
+        os.environ["PSIM_FORCE_INT_PATH"] = "1" if force_int else "0"
+        try:
+            out, paths = [], []
+            with Stepper(grid, fb.count) as st:
+                st.upload(fb)
+                for m in metas:
+                    st.set_metadata(m)
+                    st.step_async(3)
+                    st.snapshot_async()
+                    out.append(st.download().particles.copy())
+                    paths.append(st.tile_stats()["float_path"])
+            return out, paths
+        finally:
+            os.environ.pop("PSIM_FORCE_INT_PATH", None)
+
+    got, paths = run(False)
+    want, paths_int = run(True)
+    assert paths == [1, 1, 0, 1] and paths_int == [0, 0, 0, 0]
+    for k, (g, wnt) in enumerate(zip(got, want)):
+        assert np.array_equal(g["ty"], wnt["ty"])
+        dx = np.abs((g["x"].astype(np.int64) - wnt["x"].astype(np.int64) + 2**31) % 2**32 - 2**31)
+        dy = np.abs((g["y"].astype(np.int64) - wnt["y"].astype(np.int64) + 2**31) % 2**32 - 2**31)
+        assert max(dx.max(), dy.max()) <= 64 * 3 * (k + 1), (k, dx.max(), dy.max())
+        assert np.allclose(g["vx"], wnt["vx"], rtol=1e-3, atol=0.05) and np.allclose(g["vy"], wnt["vy"], rtol=1e-3, atol=0.05)
