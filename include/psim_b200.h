@@ -77,7 +77,9 @@ int psim_set_stream(PsimStepper* s, void* cuda_stream);
  * (kernel.cuh:103-115): takes a COMPACT host frame (null particles, ty < 0, are skipped), copies it
  * to the device and bins it with a stable counting sort by cell = (x >> (32-LX)) + (y >> (32-LY)) * BX.
  * Order inside a cell = input order, exactly the reference's append order (kernel.cuh:219-229).
- * The frame's metadata becomes the stepper's metadata. Synchronous w.r.t. the host. */
+ * The frame's metadata becomes the stepper's metadata. Synchronous w.r.t. the host.
+ * A frame whose metadata says DataStructure::CompactArray is ingested as the reference ingests it
+ * (frame_compact_into, kernel.cuh:207-209: input order, no binning) and stepped all-pairs from then on. */
 int psim_upload_frame(PsimStepper* s, const FrameHeader* frame);
 
 /* Same, for particle records that already live in device memory (AoS, 20 B each). */
@@ -89,7 +91,11 @@ int psim_get_metadata(const PsimStepper* s, FrameMetadata* out);
 
 /* = Kernel::run_async (kernel.cuh:139-151) for DataStructure::MatrixBuckets: enqueues one frame,
  * i.e. metadata.steps_per_frame leapfrog steps with re-binning according to the schedule, then packs
- * a snapshot of the result for psim_download_frame. Returns immediately. */
+ * a snapshot of the result for psim_download_frame. On the reference's own grid (and any grid below 1024 cells per
+ * axis) it returns immediately; on finer grids and with slabs it returns once the frame's last re-bin has been
+ * enqueued (each re-bin reads a few counts back: the tile count sizes the next launches), i.e. with the last <= 16
+ * steps still running. For DataStructure::CompactArray scenes: kernel_compact.cuh:78-92, exactly steps_per_frame
+ * all-pairs steps. */
 int psim_run_frame_async(PsimStepper* s);
 
 /* Finer-grained control (used by tests and by the driver when it needs it):
