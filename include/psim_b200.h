@@ -45,7 +45,9 @@ typedef struct PsimConfig {
     uint32_t schedule;      /* PSIM_SCHEDULE_*                                                             */
     uint32_t rebin_every;   /* native schedule only; 0 => 17 (the reference's effective cadence)           */
     int32_t device;         /* CUDA device ordinal; -1 => current device                                   */
-    uint32_t use_graph;     /* reserved, must be 0                                                         */
+    uint32_t use_graph;     /* 1: frames on grids below 1024 cells per axis (the reference's own scenes: a frame is
+                               ~150 launches of a few microseconds, launch-bound) are captured once as a CUDA graph
+                               and replayed with one cudaGraphLaunch; reference schedule, single slab            */
     /* Slab decomposition over cell rows (the reference is single-device). The grid
      * above is the GLOBAL grid; this stepper owns rows [slab_rank, slab_rank + 1) * (cells in y / slab_count)
      * and keeps one ghost row of each adjacent slab. max_particles is the capacity of the slab. */

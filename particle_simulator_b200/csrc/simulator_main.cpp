@@ -119,6 +119,7 @@ struct Simulator {
         cfg.device = opt.device;
         cfg.schedule = opt.native_schedule ? PSIM_SCHEDULE_NATIVE : PSIM_SCHEDULE_REFERENCE;
         cfg.snapshot_buffers = 2;  // frame k is copied out and sent while frame k+1 runs
+        cfg.use_graph = 1;         // small scenes are launch-bound: replay frames as CUDA graphs
         int rc = psim_create(&cfg, &stepper);
         if (rc != PSIM_OK) {
             std::fprintf(stderr, "psim_simulator: cannot create the stepper (%d): %s\n", rc, psim_last_error(nullptr));

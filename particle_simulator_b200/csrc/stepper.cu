@@ -1056,6 +1056,12 @@ struct XferOp {
 
 struct PsimGroup;
 
+struct FrameGraph {  // one captured frame (run_frame_with_graph)
+    cudaGraphExec_t exec = nullptr;
+    uint64_t steps = 0, rebins = 0, launches = 0;
+    int end_pos = 0, end_vel = 0, end_ty = 0;
+};
+
 struct PsimStepper {
     PsimConfig cfg{};
     Grid grid{};
@@ -1159,6 +1165,7 @@ struct PsimStepper {
     int native_countdown = 0;  // native schedule: steps until the next re-bin
 
     uint64_t steps_executed = 0, rebins_executed = 0, launches = 0;
+    std::map<uint32_t, FrameGraph> frame_graphs;  // PsimConfig.use_graph: captured frames by starting buffer parity
 
     bool timing = false;
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> timing_events;
@@ -1333,6 +1340,8 @@ Phys make_phys(const FrameMetadata& m, int* kernel_kn, int* kernel_frac, bool* a
     return ph;
 }
 
+void drop_frame_graphs(PsimStepper* s);
+
 // Constants of step_kernel_c (step_float.cuh). Returns false when these physics / this grid have no fp32 variant.
 bool make_phys_f(const FrameMetadata& m, const Phys& ph, const Grid& g, int kn, int frac, PhysF* out) {
     if (kn == 0 || frac == kFracEx2) return false;  // run-time exponents, MUFU.EX2 sliver: step_kernel only
@@ -1378,6 +1387,7 @@ void apply_metadata(PsimStepper* s, const FrameMetadata& m) {
     s->float_path = s->float_grid && !s->force_int_path &&
                     make_phys_f(m, s->phys, s->grid, s->kernel_kn, s->kernel_frac, &s->physf);
     s->nbr_stale = true;  // the records carry the old scale (or were not kept at all): rebuilt before the next step
+    drop_frame_graphs(s);  // captured launches carry the old constants
 }
 
 template <int KN, int FRAC>
@@ -1983,7 +1993,7 @@ int team_ingest(const Team& t, const Particle* records, uint32_t count) {
 
 // One frame (Kernel::run_async for MatrixBuckets): steps_per_frame steps with re-binning on the
 // configured schedule, then a snapshot. All slabs of a team share metadata and schedule state.
-int team_run_frame(const Team& t) {
+int team_frame_steps(const Team& t) {
     PsimStepper* lead = t.ranks[0];
     const uint32_t target = lead->meta.steps_per_frame;
     int rc;
@@ -2029,7 +2039,70 @@ int team_run_frame(const Team& t) {
         }
     }
     for (int r = 0; r < t.count; ++r) t.ranks[r]->native_countdown = lead->native_countdown;
+    return PSIM_OK;
+}
+
+int team_run_frame(const Team& t) {
+    int rc = team_frame_steps(t);
+    if (rc) return rc;
     return team_snapshot(t);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Frames as CUDA graphs (PsimConfig.use_graph). The reference's own scenes are small (<= 65 536 particles): a frame is
+// ~100 step launches and a few dozen binning launches of a few microseconds each, bound by launch overhead. On coarse
+// grids a frame needs nothing back on the host, so its launches are captured once and replayed with one
+// cudaGraphLaunch. A graph is keyed by what the launches depend on besides the metadata: which of the ping-pong
+// buffers are current when the frame starts. New metadata or a new scene drops the cache.
+// ------------------------------------------------------------------------------------------------
+bool frame_graph_usable(const PsimStepper* s) {
+    return s->cfg.use_graph && s->nranks == 1 && !s->group && !s->float_grid && !s->timing &&
+           s->cfg.schedule == PSIM_SCHEDULE_REFERENCE && s->n > 0;
+}
+
+void drop_frame_graphs(PsimStepper* s) {
+    for (auto& kv : s->frame_graphs) cudaGraphExecDestroy(kv.second.exec);
+    s->frame_graphs.clear();
+}
+
+int run_frame_with_graph(PsimStepper* s) {
+    const uint32_t key = (uint32_t)s->cur_pos | (uint32_t)s->cur_vel << 1 | (uint32_t)s->cur_ty << 2;
+    auto it = s->frame_graphs.find(key);
+    if (it == s->frame_graphs.end()) {
+        const uint64_t steps0 = s->steps_executed, rebins0 = s->rebins_executed, launches0 = s->launches;
+        CK(cudaStreamBeginCapture(s->stream, cudaStreamCaptureModeThreadLocal));
+        PsimStepper* self = s;
+        int rc = team_frame_steps(Team{&self, 1, nullptr});  // enqueues into the capture; host-side state advances as usual
+        cudaGraph_t graph = nullptr;
+        cudaError_t end = cudaStreamEndCapture(s->stream, &graph);
+        if (rc) {
+            if (graph) cudaGraphDestroy(graph);
+            return rc;
+        }
+        if (end != cudaSuccess) return fail(s, PSIM_ECUDA, "cudaStreamEndCapture failed: %s", cudaGetErrorString(end));
+        FrameGraph fg;
+        cudaError_t inst = cudaGraphInstantiate(&fg.exec, graph, 0);
+        cudaGraphDestroy(graph);
+        if (inst != cudaSuccess) return fail(s, PSIM_ECUDA, "cudaGraphInstantiate failed: %s", cudaGetErrorString(inst));
+        fg.steps = s->steps_executed - steps0;
+        fg.rebins = s->rebins_executed - rebins0;
+        fg.launches = s->launches - launches0;
+        fg.end_pos = s->cur_pos;
+        fg.end_vel = s->cur_vel;
+        fg.end_ty = s->cur_ty;
+        s->frame_graphs[key] = fg;
+        CK(cudaGraphLaunch(fg.exec, s->stream));  // the capture executed nothing
+        return PSIM_OK;
+    }
+    const FrameGraph& fg = it->second;
+    CK(cudaGraphLaunch(fg.exec, s->stream));
+    s->steps_executed += fg.steps;
+    s->rebins_executed += fg.rebins;
+    s->launches += fg.launches;
+    s->cur_pos = fg.end_pos;
+    s->cur_vel = fg.end_vel;
+    s->cur_ty = fg.end_ty;
+    return PSIM_OK;
 }
 
 Team lone(PsimStepper* const* s) { return Team{s, 1, nullptr}; }
@@ -2097,6 +2170,7 @@ void psim_destroy(PsimStepper* s) {
     }
     if (s->stream) cudaStreamSynchronize(s->stream);
     if (s->copy_stream) cudaStreamSynchronize(s->copy_stream);
+    drop_frame_graphs(s);
     if (s->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(s->comm);
     for (auto& side : s->ipc_mapped)
         for (void*& m : side)
@@ -2291,6 +2365,7 @@ int psim_set_stream(PsimStepper* s, void* cuda_stream) {
     if (rc) return rc;
     CK(cudaSetDevice(s->device));
     CK(cudaStreamSynchronize(s->stream));
+    drop_frame_graphs(s);
     s->stream = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : s->own_stream;
     return PSIM_OK;
 }
@@ -2588,7 +2663,12 @@ int psim_run_frame_async(PsimStepper* s) {
     if (rc) return rc;
     if (!s->has_scene) return fail(s, PSIM_ESTATE, "psim_run_frame_async: no scene uploaded");
     CK(cudaSetDevice(s->device));
-    rc = team_run_frame(lone(&s));
+    if (frame_graph_usable(s)) {
+        rc = run_frame_with_graph(s);
+        if (!rc) rc = enqueue_snapshot(s);
+    } else {
+        rc = team_run_frame(lone(&s));
+    }
     s->fresh_scene = false;
     return rc;
 }
