@@ -243,7 +243,20 @@ def run_ours(args, rank: int, world: int, local_rank: int) -> None:
         return a
 
     stream = torch.cuda.Stream()
-    if world == 1:
+    strong = args.scaling == "strong"
+    if strong:
+        # strong scaling (BASELINE.json configs[3]): ONE crystal of --total-particles on a fixed 8192 x 4096 grid
+        # (box 6.4 x 3.2 um), cut into `world` slabs of 4096 / world cell rows
+        rows_log2 = 12 - (world.bit_length() - 1)
+        per_slab = args.total_particles // world
+        wl = workloads.slab_crystal(rank, world, storage_factory=pinned_frame_storage, per_slab=per_slab,
+                                    rows_per_slab_log2=rows_log2, grid_x_log2=13)
+        st = Stepper(wl.grid_log2, int(1.05 * per_slab) + 65536, device=local_rank, slab_rank=rank, slab_count=world,
+                     ingest_capacity=wl.frame.count, snapshot_buffers=2)
+        if world > 1:
+            uid = slabs.broadcast_bytes(dist, Stepper.comm_unique_id() if rank == 0 else None, 128, device=dev)
+            st.comm_init(uid)
+    elif world == 1:
         wl = workloads.config_10m_solid(storage=pinned_frame_storage(3162 * 3163))
         st = Stepper(wl.grid_log2, wl.particles, device=local_rank, snapshot_buffers=2)
     else:
@@ -345,7 +358,7 @@ def run_ours(args, rank: int, world: int, local_rank: int) -> None:
         line = {
             "metric": "particle-updates/sec at 10M particles", "value": value, "unit": "particle-updates/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": wl.name, "description": wl.description, "particles": n,
                        "particles_rank0": n_local,
                        "steps_per_frame": STEPS_PER_FRAME, "leapfrog_steps_per_bench_step": executed,
@@ -353,7 +366,7 @@ def run_ours(args, rank: int, world: int, local_rank: int) -> None:
                        "l2": "state (10M x 20 B x 2 buffers = 400 MB per GPU) is larger than the 126 MB L2; "
                              "no flush",
                        "decomposition": "single slab" if world == 1 else
-                       f"{world} slabs of 2048 cell rows, one per GPU; halo (boundary rows' positions) every step: "
+                       f"{world} slabs of {st.slab_info()['rows']} cell rows, one per GPU; halo (boundary rows' positions) every step: "
                        f"{halo}; per re-bin: migrants + boundary-row cell counts + fresh ghost rows by ncclSend/ncclRecv",
                        "step_kernel": st.tile_stats()},
             "roofline": {"bound": "hbm", "kernel": "step_kernel (fused 3x3-cell force + kick + drift)",
@@ -372,7 +385,7 @@ def run_ours(args, rank: int, world: int, local_rank: int) -> None:
             "host_enqueue_ms_per_step": 1e3 * t_host / args.steps,
             "clocks": clocks,
         }
-        if world == 1 and not args.no_cpu_baseline:
+        if world == 1 and not args.no_cpu_baseline and not strong:
             st.close()  # the reference allocates its own slot arrays on this GPU
             line["cpu_baseline"] = cpu_baseline(wl, args.cpu_steps)
             line["reference_cuda_baseline"] = reference_cuda_baseline(wl, args.cpu_steps)
@@ -392,6 +405,10 @@ def main() -> None:
     ap.add_argument("--cpu-steps", type=int, default=10, help="cpu_baseline: steps_per_frame of the sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-step-timing", action="store_true", help="no CUDA events around the step-kernel launches")
+    ap.add_argument("--scaling", choices=["weak", "strong"], default="weak",
+                    help="weak (default, the metric's configuration): 10M particles per GPU; strong: --total-particles "
+                         "in one fixed 8192 x 4096-cell box cut into --gpus slabs (BASELINE.json configs[3])")
+    ap.add_argument("--total-particles", type=int, default=100_000_000)
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
