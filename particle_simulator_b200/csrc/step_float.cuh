@@ -195,9 +195,24 @@ __global__ void couple_build_kernel(const uint32_t* __restrict__ cell_start, con
     for (uint32_t m = 0; m < n; m += 2, ++k) couple_i0[k] = make_uint2((s + m) | (m + 1 < n ? 0x80000000u : 0u), c);
 }
 
-// Tiles of every owned row: ceil(couples of the row / kCouples); single block: exclusive scan into
-// tile_base[0..own_rows], total -> *total_out.
-__global__ void __launch_bounds__(1024) row_tiles_kernel(const uint32_t* __restrict__ pad_start, Grid g,
+// How many tiles a row of `m` couples gets: enough for 128 couples per tile AND for at most kTileCols occupied columns
+// per tile (a thin row -- one couple per cell -- next to a thick one would otherwise make tiles so wide that the
+// neighbour rows overflow the staging buffers); the row's couples are then split evenly over its tiles.
+constexpr int kTileCols = 64;
+__device__ __forceinline__ uint32_t tiles_of_row(const uint32_t* __restrict__ cell_start, const Grid& g, uint32_t row,
+                                                 uint32_t m) {
+    if (m == 0) return 0;
+    const uint32_t c0 = row << g.lx, p0 = cell_start[c0], p1 = cell_start[c0 + g.bx];
+    // first occupied column: the last cell whose start is still p0; last occupied: the last cell that starts below p1
+    const uint32_t first = (uint32_t)last_le(cell_start + c0, (int)g.bx, p0);
+    const uint32_t last = (uint32_t)last_le(cell_start + c0, (int)g.bx, p1 - 1);
+    const uint32_t cols = last - first + 1;
+    return max((m + kCouples - 1) / kCouples, (cols + kTileCols - 1) / kTileCols);
+}
+
+// Tiles of every owned row (tiles_of_row); single block: exclusive scan into tile_base[0..own_rows], total -> *total_out.
+__global__ void __launch_bounds__(1024) row_tiles_kernel(const uint32_t* __restrict__ cell_start,
+                                                         const uint32_t* __restrict__ pad_start, Grid g,
                                                          uint32_t* __restrict__ tile_base, uint32_t* __restrict__ total_out) {
     __shared__ uint32_t warp_sum[32];
     __shared__ uint32_t carry;
@@ -209,7 +224,7 @@ __global__ void __launch_bounds__(1024) row_tiles_kernel(const uint32_t* __restr
         if (r < g.own_rows) {
             const uint32_t row = g.own_row0 + r;
             const uint32_t m = (pad_start[(row + 1) << g.lx] - pad_start[row << g.lx]) >> 1;
-            v = (m + kCouples - 1) / kCouples;
+            v = tiles_of_row(cell_start, g, row, m);
         }
         uint32_t incl = v;
         for (int o = 1; o < 32; o <<= 1) {
@@ -249,10 +264,18 @@ __global__ void tile_build_kernel(const uint32_t* __restrict__ cell_start, const
     const uint32_t r = (uint32_t)last_le(tile_base, (int)g.own_rows, b);
     const uint32_t row = g.own_row0 + r;
     const uint32_t row_k0 = pad_start[row << g.lx] >> 1, row_k1 = pad_start[(row + 1) << g.lx] >> 1;
+    const uint32_t row_tiles = tile_base[r + 1] - tile_base[r];
+    const uint32_t per_tile = (row_k1 - row_k0 + row_tiles - 1) / row_tiles;  // <= kCouples, even split
     TileC t;
-    t.k0 = row_k0 + (b - tile_base[r]) * kCouples;
-    t.nk = min(row_k1 - t.k0, (uint32_t)kCouples);
+    t.k0 = row_k0 + (b - tile_base[r]) * per_tile;
+    t.nk = t.k0 < row_k1 ? min(row_k1 - t.k0, per_tile) : 0u;  // the even split can leave a row's last tile empty
     t.row = row;
+    if (t.nk == 0) {  // nothing to step: no staging either
+        t.fits = 0;
+        for (int d = 0; d < 3; ++d) t.cs_lo[d] = t.cs_cnt[d] = t.p_lo[d] = t.p_cnt[d] = 0;
+        tiles[b] = t;
+        return;
+    }
     const uint32_t c_first = couple_i0[t.k0].y & (g.bx - 1);
     const uint32_t c_last = couple_i0[t.k0 + t.nk - 1].y & (g.bx - 1);
     const uint32_t col_lo = c_first == 0 ? 0 : c_first - 1;

@@ -1608,7 +1608,7 @@ int enqueue_scan(PsimStepper* s) {
         scan_top_kernel<<<1, 1024, 0, s->stream>>>(s->block_sum, blocks, s->pad_start + cells);
         scan_apply_kernel<true><<<blocks, kScanThreads, 0, s->stream>>>(s->cell_count, cells, s->block_sum, s->pad_start);
         couple_build_kernel<<<div_up(cells, 256), 256, 0, s->stream>>>(s->cell_start, s->pad_start, cells, s->couple_i0);
-        row_tiles_kernel<<<1, 1024, 0, s->stream>>>(s->pad_start, s->grid, s->tile_base, s->d_couple_tiles);
+        row_tiles_kernel<<<1, 1024, 0, s->stream>>>(s->cell_start, s->pad_start, s->grid, s->tile_base, s->d_couple_tiles);
         s->launches += 5;
     }
     CK(cudaGetLastError());
@@ -2324,7 +2324,9 @@ int psim_create(const PsimConfig* config, PsimStepper** out) {
     if (st->float_grid) {
         // couples: every particle, plus one half-empty couple per cell at most
         const size_t couples = (cap_total + std::min<size_t>(cap_total, g.cells)) / 2 + 1;
-        st->tiles_c_cap = (uint32_t)((cap + std::min<size_t>(cap, (size_t)g.own_rows * g.bx)) / 2 / kCouples + g.own_rows + 1);
+        // per row: ceil(couples / 128) or ceil(occupied columns / kTileCols), whichever is larger
+        st->tiles_c_cap = (uint32_t)((cap + std::min<size_t>(cap, (size_t)g.own_rows * g.bx)) / 2 / kCouples + g.own_rows + 1 +
+                                     (size_t)g.own_rows * (g.bx / kTileCols + 1));
         CKC(cudaMalloc(&st->pad_start, sizeof(uint32_t) * ((size_t)g.cells + 1 + kPadCells)));
         CKC(cudaMemset(st->pad_start, 0, sizeof(uint32_t) * ((size_t)g.cells + 1 + kPadCells)));
         CKC(cudaMalloc(&st->couple_i0, sizeof(uint2) * couples));
