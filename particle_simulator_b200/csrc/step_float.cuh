@@ -178,8 +178,8 @@ __global__ void __launch_bounds__(kCouples, 9) step_kernel_c(const StepArgs a, c
             else pairc<KN, FRAC, false>(j.x, j.y, nx, ny, pf, gx, gy);
         }
     }
-    finish_particle(i0, p0, v0, cell, gx.x, gy.x, pf.pair_scale, pf.pair_scale, a);
-    if (has1) finish_particle(i1, p1, v1, cell, gx.y, gy.y, pf.pair_scale, pf.pair_scale, a);
+    finish_particle<true>(i0, p0, v0, cell, gx.x, gy.x, pf.pair_scale, pf.pair_scale, a);  // KN > 0 implies m == 6
+    if (has1) finish_particle<true>(i1, p1, v1, cell, gx.y, gy.y, pf.pair_scale, pf.pair_scale, a);
 }
 
 // ---- re-bin side of the couples ------------------------------------------------------------------------

@@ -92,6 +92,7 @@ struct Phys {
     float ux, uy;        // dt * 2^32 / box: velocity -> fixed-point displacement per step
     float cursor_x, cursor_y, cursor_r2;  // cursor_r2 = cursor_size^2 / 4
     int wall_m6;         // m == 6: wall term by multiplication
+    int cursor_on;       // the cursor can reach a particle of the box at all
     float m;
 };
 
@@ -276,11 +277,13 @@ __device__ __forceinline__ void window_accumulate(const uint2* __restrict__ pj, 
 }
 
 // Repulsive wall term C eps m (sigma/d)^m / d (particle.cuh:68-71).
+// M6: m == 6 is known at compile time (every kernel variant with compile-time powers): no predicated-off MUFU pair.
+template <bool M6>
 __device__ __forceinline__ float wall_term(float d, const Phys& ph) {
     float inv_d = fast_rcp(d);
     float q = ph.sigma * inv_d;
     float pw;
-    if (ph.wall_m6) {
+    if (M6 || ph.wall_m6) {
         float q2 = q * q;
         pw = q2 * q2 * q2;
     } else {
@@ -290,21 +293,24 @@ __device__ __forceinline__ float wall_term(float d, const Phys& ph) {
 }
 
 // Cursor + wall forces on one particle (kernel_bucket.cuh:54-69, particle.cuh:125-144).
+template <bool M6>
 __device__ __forceinline__ float2 field_force(uint2 p, const Phys& ph) {
     const float inv32 = 1.f / 4294967296.f;
     float2 f = make_float2(0.f, 0.f);
-    float dx = ph.cursor_x - __uint2float_rn(p.x) * inv32;
-    float dy = ph.cursor_y - __uint2float_rn(p.y) * inv32;
-    float sq = dx * dx + dy * dy;
-    if (sq < ph.cursor_r2) {
-        float c = 8e-12f * fast_rcp(sq + 1.f);
-        f.x = dx > 0 ? -c : c;
-        f.y = dy > 0 ? -c : c;
+    if (ph.cursor_on) {  // uniform: the editor parks the cursor at (-1, -1), out of reach of every particle
+        float dx = ph.cursor_x - __uint2float_rn(p.x) * inv32;
+        float dy = ph.cursor_y - __uint2float_rn(p.y) * inv32;
+        float sq = dx * dx + dy * dy;
+        if (sq < ph.cursor_r2) {
+            float c = 8e-12f * fast_rcp(sq + 1.f);
+            f.x = dx > 0 ? -c : c;
+            f.y = dy > 0 ? -c : c;
+        }
     }
-    if (p.x < 0xFFFFFFFFu / 2) f.x += wall_term(__uint2float_rn(p.x) * ph.kx, ph);
-    else f.x -= wall_term(__uint2float_rn(0xFFFFFFFFu - p.x) * ph.kx, ph);
-    if (p.y < 0xFFFFFFFFu / 2) f.y += wall_term(__uint2float_rn(p.y) * ph.ky, ph);
-    else f.y -= wall_term(__uint2float_rn(0xFFFFFFFFu - p.y) * ph.ky, ph);
+    if (p.x < 0xFFFFFFFFu / 2) f.x += wall_term<M6>(__uint2float_rn(p.x) * ph.kx, ph);
+    else f.x -= wall_term<M6>(__uint2float_rn(0xFFFFFFFFu - p.x) * ph.kx, ph);
+    if (p.y < 0xFFFFFFFFu / 2) f.y += wall_term<M6>(__uint2float_rn(p.y) * ph.ky, ph);
+    else f.y -= wall_term<M6>(__uint2float_rn(0xFFFFFFFFu - p.y) * ph.ky, ph);
     return f;
 }
 
@@ -507,9 +513,10 @@ __global__ void halo_publish_kernel(StepArgs a) {
 }
 
 // Cursor + wall force, pair sum, kick + drift and the two stores of one particle (shared by all step kernels).
+template <bool M6 = false>
 __device__ __forceinline__ void finish_particle(uint32_t i, uint2 pi, float2 vi, uint32_t cell, float sum_x, float sum_y,
                                                 float scale_x, float scale_y, const StepArgs& a) {
-    float2 f = field_force(pi, a.ph);
+    float2 f = field_force<M6>(pi, a.ph);
     f.x = fmaf(scale_x, sum_x, f.x);
     f.y = fmaf(scale_y, sum_y, f.y);
     uint2 po;
@@ -543,7 +550,7 @@ __device__ __forceinline__ void step_particle(uint32_t i, uint2 pi, float2 vi, u
         if (d == 1) window_accumulate<KN, FRAC, ANISO, true, CG>(win, (int)(e - s), pi, a.ph, gx, gy);  // contains i
         else window_accumulate<KN, FRAC, ANISO, false, CG>(win, (int)(e - s), pi, a.ph, gx, gy);
     }
-    finish_particle(i, pi, vi, cell, gx.x + gx.y, gy.x + gy.y, a.ph.pair_scale, a.ph.pair_scale_y, a);
+    finish_particle<(KN > 0)>(i, pi, vi, cell, gx.x + gx.y, gy.x + gy.y, a.ph.pair_scale, a.ph.pair_scale_y, a);
 }
 
 template <int KN, int FRAC, bool ANISO>
@@ -1310,6 +1317,11 @@ Phys make_phys(const FrameMetadata& m, int* kernel_kn, int* kernel_frac, bool* a
     ph.cursor_x = m.cursor_pos[0];
     ph.cursor_y = m.cursor_pos[1];
     ph.cursor_r2 = m.cursor_size * m.cursor_size / 4;
+    {   // particles live in [0, 1)^2 of cursor units: the cursor matters only if its disc meets that square
+        const float r = std::sqrt(std::max(ph.cursor_r2, 0.f));
+        const bool reach = ph.cursor_x > -r && ph.cursor_x < 1.f + r && ph.cursor_y > -r && ph.cursor_y < 1.f + r;
+        ph.cursor_on = reach && ph.cursor_r2 > 0.f ? 1 : 0;
+    }
 
     // Which step-kernel variant evaluates these exponents.
     //   m = 6 and 5 <= kn <= 10: the integer powers are compile-time products (KN = kn);
