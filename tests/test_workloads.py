@@ -38,3 +38,31 @@ def test_slab_crystal_rows_partition_the_crystal():
         p = w.frame.particles
         owned += int((slab_of(p["y"], 4, ly) == r).sum())  # each rank is handed a little more than its own rows
     assert owned == geo["nx"] * geo["ny"]
+
+
+def test_presets_round_trip_a_scene():
+    """Preset::{from_frame, to_frame} and the Presets list (particle_io/src/presets.rs:84-154)."""
+    from particle_simulator_b200 import io
+    from particle_simulator_b200.frame import FrameBuffer, default_metadata
+    from particle_simulator_b200.presets import Preset, Presets
+
+    fb = FrameBuffer(40)
+    fb.metadata["box_width"], fb.metadata["box_height"] = 30e-9, 20e-9
+    fb.metadata["particles"][1] = (3.2e-10, 0.9e-21, 11.0, 5.0)
+    fb.metadata["steps_per_frame"] = 7  # not part of a preset
+    io.scene_hex_square(fb, 5, 4, (15e-9, 10e-9), 1.0, 5.0, 5.0, 1, seed=1)
+    p = Preset.from_frame("droplet", fb)
+    back = p.to_frame()
+    assert back.count == 20 and back.particles.tobytes() == fb.particles.tobytes()
+    assert float(back.metadata["box_width"]) == np.float32(30e-9) and float(back.metadata["box_height"]) == np.float32(20e-9)
+    assert back.metadata["particles"].tobytes() == fb.metadata["particles"].tobytes()
+    assert int(back.metadata["steps_per_frame"]) == int(default_metadata()["steps_per_frame"])
+    lib = Presets()
+    lib.add_preset(p)
+    lib.add_preset(Preset.from_frame("again", back))
+    assert lib.get_presets_len() == 2 and lib.get_preset(1).name == "again"
+    lib.change_preset(p, 5)  # past the end: ignored
+    lib.change_preset(Preset.from_frame("renamed", back), 0)
+    assert lib.get_preset(0).name == "renamed"
+    lib.delete_preset(0)
+    assert lib.get_presets_len() == 1 and lib.get_preset(0).name == "again"
