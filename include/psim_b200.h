@@ -53,14 +53,23 @@ typedef struct PsimConfig {
      * and keeps one ghost row of each adjacent slab. max_particles is the capacity of the slab. */
     uint32_t slab_rank;        /* 0 .. slab_count-1                                                        */
     uint32_t slab_count;       /* 0 or 1 => the whole grid                                                 */
-    uint32_t ghost_capacity;   /* particles one ghost row can hold; 0 => 4x the slab's mean row, >= 4096   */
-    uint32_t migrant_capacity; /* particles that can move to ONE neighbour slab in one re-bin; 0 => same   */
+    uint32_t ghost_capacity;   /* particles one ghost row can hold; 0 => 4x the mean row of a full slab as thin as the
+                                  thinnest of this slab and its neighbours, >= 4096                        */
+    uint32_t migrant_capacity; /* particles that can move to ONE neighbour slab in one re-bin, the same on every
+                                  slab; 0 => 4x the mean row of a full slab of average height, >= 4096     */
     uint32_t ingest_capacity;  /* records an uploaded frame can hold (a slab is usually handed the whole
                                   scene and keeps its own rows); 0 => max_particles                        */
     uint32_t snapshot_buffers; /* 0 or 1: one snapshot buffer; 2: two that alternate, so that the snapshot of the
                                   previous frame can be downloaded (psim_download_frame_ex, age 1) while the next
                                   frame, its snapshot included, is already enqueued -- the double buffering of the
                                   reference's main loop (cuda_simulator.cu:28-37)                           */
+    uint32_t slab_bounds[4];   /* all 0: slabs own equal shares of the cell rows. Otherwise global cell rows
+                                  {first row of the slab below, first own row, end of the own rows = first row of
+                                  the slab above, end of the slab above}: entries k-1 .. k+2 of one array of
+                                  slab_count + 1 boundaries every slab takes its four from (clamped at the ends:
+                                  slab 0 has {0, 0, ..}, the last slab {.., rows, rows}), e.g. from
+                                  psim_balance_rows. Every slab owns at least 2 rows; adjacent slabs must meet
+                                  (checked by psim_group_create / psim_comm_init).                          */
 } PsimConfig;
 
 /* Defaults: 64x64 cells (the reference grid), 65536 particles, reference schedule, device -1. */
@@ -171,6 +180,15 @@ typedef struct PsimTileStats {
     uint64_t threads_live, threads_launched;
 } PsimTileStats;
 int psim_tile_stats(PsimStepper* s, PsimTileStats* out);
+
+/* Row boundaries that give every slab about the same number of live particles of `scene` (SURVEY.md section 8e:
+ * a clustered scene cut into equal numbers of rows is badly balanced). Host code, no GPU involved: a histogram of
+ * cell rows (row = y >> (32 - grid_y_log2), kernel.cuh:225), cut at the multiples of count / slab_count, every slab
+ * at least 2 rows. bounds[0] = 0 <= ... <= bounds[slab_count] = 1 << grid_y_log2; slab k's PsimConfig.slab_bounds are
+ * bounds[k-1 .. k+2] clamped to the array (psim_slab_bounds_of). Re-balancing a running decomposition = download,
+ * psim_balance_rows on the snapshot, re-create the steppers, upload. */
+int psim_balance_rows(const FrameHeader* scene, uint32_t grid_y_log2, uint32_t slab_count, uint32_t* bounds);
+void psim_slab_bounds_of(const uint32_t* bounds, uint32_t slab_rank, uint32_t slab_count, uint32_t out[4]);
 
 /* Where this stepper's slab sits and what it currently holds. */
 typedef struct PsimSlabInfo {

@@ -57,6 +57,7 @@ struct Grid {
     int32_t row_offset;  // local row = global row - row_offset
     uint32_t own_row0;   // first owned local row (1 when there is a lower ghost row, else 0)
     uint32_t own_rows;   // owned rows
+    uint32_t rows_below, rows_above;  // rows the adjacent slabs own (0: no such slab): how far a migrant can be delivered
 };
 
 // Where a position falls relative to the rows this stepper owns.
@@ -976,8 +977,8 @@ __global__ void migrant_extract_kernel(const uint2* __restrict__ pos, uint32_t o
     uint32_t key = cell_of(p, g);
     if (key < kKeyUp) return;
     int32_t row = (int32_t)(p.y >> g.sy) - g.row_offset;
-    // the neighbours' slabs are as tall as this one: anything beyond them cannot be delivered
-    if (row < (int32_t)g.own_row0 - (int32_t)g.own_rows || row >= (int32_t)(g.own_row0 + 2 * g.own_rows))
+    // anything beyond the adjacent slabs cannot be delivered
+    if (row < (int32_t)g.own_row0 - (int32_t)g.rows_below || row >= (int32_t)(g.own_row0 + g.own_rows + g.rows_above))
         atomicOr(flags, kErrMigrantTooFar);
     uint32_t dir = key == kKeyDown ? 0u : 1u;
     uint32_t slot = atomicAdd(&counters[dir], 1u);
@@ -2248,9 +2249,29 @@ int psim_create(const PsimConfig* config, PsimStepper** out) {
     const uint32_t nranks = config->slab_count ? config->slab_count : 1;
     const uint32_t rows_global = 1u << config->grid_y_log2;
     if (config->slab_rank >= nranks) return fail(s, PSIM_EINVAL, "psim_create: slab_rank %u of %u", config->slab_rank, nranks);
-    if (rows_global % nranks != 0 || rows_global / nranks < 2)
-        return fail(s, PSIM_EINVAL, "psim_create: %u cell rows do not split into %u slabs of at least 2 rows", rows_global,
-                    nranks);
+    // Rows of this slab and of the two adjacent ones: PsimConfig.slab_bounds, or equal shares of the rows.
+    uint32_t bounds[4];
+    std::memcpy(bounds, config->slab_bounds, sizeof bounds);
+    if (bounds[2] == 0) {
+        if (rows_global % nranks != 0 || rows_global / nranks < 2)
+            return fail(s, PSIM_EINVAL, "psim_create: %u cell rows do not split into %u slabs of at least 2 rows "
+                        "(or give PsimConfig.slab_bounds)", rows_global, nranks);
+        const uint32_t per = rows_global / nranks, r = config->slab_rank;
+        bounds[0] = r > 0 ? (r - 1) * per : 0;
+        bounds[1] = r * per;
+        bounds[2] = (r + 1) * per;
+        bounds[3] = r + 1 < nranks ? (r + 2) * per : rows_global;
+    }
+    {
+        const bool first = config->slab_rank == 0, last = config->slab_rank + 1 == nranks;
+        const bool ok = bounds[0] <= bounds[1] && bounds[1] + 2 <= bounds[2] && bounds[2] <= bounds[3] && bounds[3] <= rows_global &&
+                        (first ? bounds[0] == 0 && bounds[1] == 0 : bounds[0] + 2 <= bounds[1]) &&
+                        (last ? bounds[2] == rows_global && bounds[3] == rows_global : bounds[2] + 2 <= bounds[3]);
+        if (!ok)
+            return fail(s, PSIM_EINVAL, "psim_create: slab_bounds {%u, %u, %u, %u} of slab %u of %u: every slab owns at least 2 "
+                        "cell rows, the first starts at row 0, the last ends at row %u", bounds[0], bounds[1], bounds[2], bounds[3],
+                        config->slab_rank, nranks, rows_global);
+    }
 
     int device = config->device;
     int ndev = 0;
@@ -2280,19 +2301,26 @@ int psim_create(const PsimConfig* config, PsimStepper** out) {
     g.bx = 1u << g.lx;
     g.sx = 32 - g.lx;
     g.sy = 32 - config->grid_y_log2;
-    g.own_rows = rows_global / nranks;
+    std::memcpy(st->cfg.slab_bounds, bounds, sizeof bounds);
+    g.own_rows = bounds[2] - bounds[1];
+    g.rows_below = bounds[1] - bounds[0];
+    g.rows_above = bounds[3] - bounds[2];
     g.own_row0 = st->rank > 0 ? 1 : 0;
     g.by = g.own_rows + g.own_row0 + (st->rank + 1 < st->nranks ? 1 : 0);
-    g.row_offset = (int32_t)(st->rank * g.own_rows) - (int32_t)g.own_row0;
+    g.row_offset = (int32_t)bounds[1] - (int32_t)g.own_row0;
     g.cells = g.bx * g.by;
 
     const size_t cap = config->max_particles;
     if (nranks > 1) {
-        // a ghost row holds one cell row of a neighbour: by default as many particles as this slab's rows
-        // hold on average, times 4, and at least 4096
-        uint32_t dflt = (uint32_t)std::min<size_t>(cap, std::max<size_t>(4096, 4 * (cap / g.own_rows + 1)));
-        st->ghost_cap = config->ghost_capacity ? config->ghost_capacity : dflt;
-        st->box_capacity = config->migrant_capacity ? config->migrant_capacity : dflt;
+        // A ghost row holds one cell row of a neighbour: by default 4 times what a row holds on average when the
+        // thinnest of the three slabs involved is full, and at least 4096. The migrant boxes are the same size on
+        // every slab (they are exchanged): 4 times the mean row of a slab of average height.
+        auto rows_of = [&](uint32_t rows) { return (uint32_t)std::min<size_t>(cap, std::max<size_t>(4096, 4 * (cap / rows + 1))); };
+        uint32_t thinnest = g.own_rows;
+        if (g.rows_below) thinnest = std::min(thinnest, g.rows_below);
+        if (g.rows_above) thinnest = std::min(thinnest, g.rows_above);
+        st->ghost_cap = config->ghost_capacity ? config->ghost_capacity : rows_of(thinnest);
+        st->box_capacity = config->migrant_capacity ? config->migrant_capacity : rows_of(std::max(rows_global / nranks, 1u));
     }
     st->cap_total = (uint32_t)std::min<size_t>(cap + 2 * (size_t)st->ghost_cap, 0x7FFFFF00u);
     st->box_bytes = sizeof(MigrantBoxHeader) + sizeof(Particle) * (size_t)st->box_capacity;
@@ -2402,7 +2430,7 @@ struct HaloExport {
     cudaIpcMemHandle_t nbr[2];  // fine grids only
     uint32_t valid;
     uint32_t has_nbr;
-    uint32_t _pad[2];
+    uint32_t row_begin, row_end;  // the exporter's own rows: adjacent slabs must meet
 };
 
 // Map the neighbours' buffers (one process per slab). Collective over the communicator. Any failure on any
@@ -2424,6 +2452,8 @@ int connect_peers(PsimStepper* s) {
         cudaGetLastError();
     }
     mine.valid = ok ? 1u : 0u;
+    mine.row_begin = s->cfg.slab_bounds[1];
+    mine.row_end = s->cfg.slab_bounds[2];
     HaloExport* d_io = nullptr;  // [0] mine, [1] from the lower, [2] from the upper neighbour
     int* d_ok = nullptr;
     CK(cudaMalloc(&d_io, 3 * sizeof(HaloExport)));
@@ -2442,6 +2472,13 @@ int connect_peers(PsimStepper* s) {
     HaloExport got[3];
     CK(cudaMemcpyAsync(got, d_io, sizeof got, cudaMemcpyDeviceToHost, s->stream));
     CK(cudaStreamSynchronize(s->stream));
+    bool rows_meet = true;
+    for (int side = 0; side < 2; ++side) {
+        if (side == 0 ? !(s->rank > 0) : !(s->rank + 1 < s->nranks)) continue;
+        const HaloExport& e = got[1 + side];
+        rows_meet = rows_meet && (side == 0 ? e.row_end == s->cfg.slab_bounds[1] && e.row_begin == s->cfg.slab_bounds[0]
+                                            : e.row_begin == s->cfg.slab_bounds[2] && e.row_end == s->cfg.slab_bounds[3]);
+    }
     for (int side = 0; side < 2 && ok; ++side) {
         if (side == 0 ? !(s->rank > 0) : !(s->rank + 1 < s->nranks)) continue;
         const HaloExport& e = got[1 + side];
@@ -2460,13 +2497,17 @@ int connect_peers(PsimStepper* s) {
             }
         }
     }
-    // everybody pushes or nobody does
+    // everybody pushes or nobody does (-1: somebody's rows do not meet its neighbour's, nobody may run)
+    if (!rows_meet) ok = -1;
     CK(cudaMemcpyAsync(d_ok, &ok, sizeof ok, cudaMemcpyHostToDevice, s->stream));
     CKN(g_nccl.AllReduce(d_ok, d_ok, 1, kNcclInt32, kNcclMin, s->comm, s->stream));
     CK(cudaMemcpyAsync(&ok, d_ok, sizeof ok, cudaMemcpyDeviceToHost, s->stream));
     CK(cudaStreamSynchronize(s->stream));
     cudaFree(d_io);
     cudaFree(d_ok);
+    if (ok < 0)
+        return fail(s, PSIM_EINVAL, "psim_comm_init: the slab_bounds of adjacent ranks do not meet (slab %d owns rows [%u, %u))",
+                    s->rank, s->cfg.slab_bounds[1], s->cfg.slab_bounds[2]);
     s->push = ok != 0;
     if (s->push) {
         for (int side = 0; side < 2; ++side) {
@@ -2847,12 +2888,48 @@ int psim_device_state(PsimStepper* s, const void** pos, const void** vel, const 
     return PSIM_OK;
 }
 
+int psim_balance_rows(const FrameHeader* scene, uint32_t grid_y_log2, uint32_t slab_count, uint32_t* bounds) {
+    PsimStepper* s = nullptr;
+    if (!scene || !bounds || slab_count == 0 || grid_y_log2 < 3 || grid_y_log2 > 15 || (2ull * slab_count) > (1ull << grid_y_log2))
+        return fail(s, PSIM_EINVAL, "psim_balance_rows: bad argument (every slab needs 2 of the %llu cell rows)",
+                    1ull << (grid_y_log2 & 31));
+    const uint32_t rows = 1u << grid_y_log2;
+    std::vector<uint64_t> upto(rows + 1, 0);  // live particles in rows < r
+    const Particle* p = scene->particles;
+    uint64_t live = 0;
+    for (uint32_t i = 0; i < scene->particle_count; ++i)
+        if (p[i].ty >= 0) {
+            upto[(p[i].y >> (32 - grid_y_log2)) + 1] += 1;
+            live += 1;
+        }
+    for (uint32_t r = 0; r < rows; ++r) upto[r + 1] += upto[r];
+    bounds[0] = 0;
+    bounds[slab_count] = rows;
+    for (uint32_t k = 1; k < slab_count; ++k) {
+        // the boundary whose share of the particles is nearest to k / slab_count
+        const uint64_t want = live * k / slab_count;
+        uint32_t r = (uint32_t)(std::lower_bound(upto.begin(), upto.end(), want) - upto.begin());
+        if (r > 0 && want - upto[r - 1] < upto[std::min(r, rows)] - want) r -= 1;
+        bounds[k] = std::min(r, rows);
+    }
+    for (uint32_t k = 1; k < slab_count; ++k) bounds[k] = std::max(bounds[k], bounds[k - 1] + 2);
+    for (uint32_t k = slab_count - 1; k >= 1; --k) bounds[k] = std::min(bounds[k], bounds[k + 1] - 2);
+    return PSIM_OK;
+}
+
+void psim_slab_bounds_of(const uint32_t* bounds, uint32_t slab_rank, uint32_t slab_count, uint32_t out[4]) {
+    out[0] = bounds[slab_rank > 0 ? slab_rank - 1 : 0];
+    out[1] = bounds[slab_rank];
+    out[2] = bounds[slab_rank + 1];
+    out[3] = bounds[std::min(slab_rank + 2, slab_count)];
+}
+
 int psim_slab_info(const PsimStepper* s, PsimSlabInfo* out) {
     if (!s || !out) return PSIM_EINVAL;
     std::memset(out, 0, sizeof *out);
     out->slab_rank = (uint32_t)s->rank;
     out->slab_count = (uint32_t)s->nranks;
-    out->first_row = (uint32_t)(s->rank * (int)s->grid.own_rows);
+    out->first_row = s->cfg.slab_bounds[1];
     out->rows = s->grid.own_rows;
     out->local_rows = s->grid.by;
     out->first_local_row = (uint32_t)((int32_t)out->first_row - (int32_t)s->grid.own_row0);
@@ -2878,9 +2955,13 @@ int psim_group_create(PsimStepper* const* steppers, uint32_t count, PsimGroup** 
             m->device != steppers[0]->device || m->cfg.grid_x_log2 != steppers[0]->cfg.grid_x_log2 ||
             m->cfg.grid_y_log2 != steppers[0]->cfg.grid_y_log2 || m->cfg.schedule != steppers[0]->cfg.schedule ||
             m->cfg.rebin_every != steppers[0]->cfg.rebin_every || m->box_capacity != steppers[0]->box_capacity ||
-            m->ingest_cap != steppers[0]->ingest_cap)  // every slab scans the whole ingested frame
+            m->ingest_cap != steppers[0]->ingest_cap ||  // every slab scans the whole ingested frame
+            (r > 0 && (m->cfg.slab_bounds[1] != steppers[r - 1]->cfg.slab_bounds[2] ||
+                       m->cfg.slab_bounds[0] != steppers[r - 1]->cfg.slab_bounds[1] ||
+                       m->cfg.slab_bounds[2] != steppers[r - 1]->cfg.slab_bounds[3])))  // adjacent slabs meet
             return fail(s, PSIM_EINVAL, "psim_group_create: stepper %u must be slab %u of %u on the group's device "
-                        "with the group's grid, schedule and capacities (ingest_capacity included)", r, r, count);
+                        "with the group's grid, schedule and capacities (ingest_capacity included), its rows starting where slab %u's end",
+                        r, r, count, r ? r - 1 : 0);
     }
     CK(cudaSetDevice(steppers[0]->device));
     PsimGroup* g = new PsimGroup;

@@ -47,6 +47,7 @@ class CConfig(ctypes.Structure):
         ("migrant_capacity", ctypes.c_uint32),
         ("ingest_capacity", ctypes.c_uint32),
         ("snapshot_buffers", ctypes.c_uint32),
+        ("slab_bounds", ctypes.c_uint32 * 4),
     ]
 
 
@@ -78,6 +79,9 @@ def lib() -> ctypes.CDLL:
         L.psim_create.argtypes = [ctypes.POINTER(CConfig), ctypes.POINTER(vp)]
         L.psim_destroy.restype = None
         L.psim_destroy.argtypes = [vp]
+        L.psim_slab_bounds_of.restype = None
+        L.psim_slab_bounds_of.argtypes = [ctypes.POINTER(ctypes.c_uint32), ctypes.c_uint32, ctypes.c_uint32,
+                                          ctypes.POINTER(ctypes.c_uint32)]
         L.psim_last_error.restype = ctypes.c_char_p
         L.psim_last_error.argtypes = [vp]
         for name, args in {
@@ -107,6 +111,7 @@ def lib() -> ctypes.CDLL:
             "psim_comm_unique_id": [vp],
             "psim_comm_init": [vp, vp],
             "psim_group_create": [ctypes.POINTER(vp), ctypes.c_uint32, ctypes.POINTER(vp)],
+            "psim_balance_rows": [vp, ctypes.c_uint32, ctypes.c_uint32, ctypes.POINTER(ctypes.c_uint32)],
             "psim_group_upload_frame": [vp, vp],
             "psim_group_set_metadata": [vp, vp],
             "psim_group_run_frame_async": [vp],
@@ -141,7 +146,9 @@ class Stepper:
     def __init__(self, grid_log2: tuple[int, int] = (6, 6), max_particles: int = 65536,
                  schedule: int = SCHEDULE_REFERENCE, rebin_every: int = 0, device: int = -1,
                  use_graph: bool = False, slab_rank: int = 0, slab_count: int = 1, ghost_capacity: int = 0,
-                 migrant_capacity: int = 0, ingest_capacity: int = 0, snapshot_buffers: int = 1):
+                 migrant_capacity: int = 0, ingest_capacity: int = 0, snapshot_buffers: int = 1,
+                 bounds=None):
+        """`bounds`: slab_count + 1 cell-row boundaries shared by all slabs (balance_rows); None: equal shares."""
         L = lib()
         cfg = L.psim_default_config()
         cfg.grid_x_log2, cfg.grid_y_log2 = grid_log2
@@ -153,6 +160,12 @@ class Stepper:
         cfg.slab_rank, cfg.slab_count = slab_rank, slab_count
         cfg.ghost_capacity, cfg.migrant_capacity, cfg.ingest_capacity = ghost_capacity, migrant_capacity, ingest_capacity
         cfg.snapshot_buffers = snapshot_buffers
+        if bounds is not None:
+            b = [int(v) for v in bounds]
+            if len(b) != slab_count + 1:
+                raise ValueError(f"{slab_count} slabs have {slab_count + 1} row boundaries, got {len(b)}")
+            arr = (ctypes.c_uint32 * (slab_count + 1))(*b)
+            L.psim_slab_bounds_of(arr, slab_rank, slab_count, cfg.slab_bounds)
         self._h = ctypes.c_void_p()
         rc = L.psim_create(ctypes.byref(cfg), ctypes.byref(self._h))
         if rc != 0:
@@ -310,6 +323,16 @@ class Stepper:
         return ms.value, n.value
 
 
+def balance_rows(frame: FrameBuffer, grid_y_log2: int, slab_count: int) -> list[int]:
+    """psim_balance_rows: slab_count + 1 cell-row boundaries that give every slab about the same number of the
+    frame's live particles (host code; needs no GPU)."""
+    out = (ctypes.c_uint32 * (slab_count + 1))()
+    rc = lib().psim_balance_rows(frame.ptr, grid_y_log2, slab_count, out)
+    if rc != 0:
+        raise PsimError(f"psim_balance_rows failed ({rc}): {lib().psim_last_error(None).decode()}")
+    return list(out)
+
+
 class SlabGroup:
     """All slabs of a row decomposition inside one process on one device (psim_group_*): the same
     slabs, halo exchange and migration as the one-process-per-GPU NCCL mode, with device-to-device
@@ -317,11 +340,18 @@ class SlabGroup:
 
     def __init__(self, grid_log2: tuple[int, int], slab_count: int, max_particles_per_slab: int,
                  ingest_capacity: int = 0, schedule: int = SCHEDULE_REFERENCE, rebin_every: int = 0, device: int = -1,
-                 ghost_capacity: int = 0, migrant_capacity: int = 0):
-        self.slabs = [Stepper(grid_log2, max_particles_per_slab, schedule, rebin_every, device, slab_rank=r,
-                              slab_count=slab_count, ghost_capacity=ghost_capacity,
-                              migrant_capacity=migrant_capacity, ingest_capacity=ingest_capacity)
-                      for r in range(slab_count)]
+                 ghost_capacity: int = 0, migrant_capacity: int = 0, bounds=None):
+        """`bounds`: slab_count + 1 cell-row boundaries (balance_rows(scene, ...)); None: equal numbers of rows."""
+        self.grid_log2, self.bounds = grid_log2, None if bounds is None else [int(b) for b in bounds]
+        self._make = lambda r, bnds, cap: Stepper(grid_log2, cap, schedule, rebin_every, device, slab_rank=r,
+                                                  slab_count=slab_count, ghost_capacity=ghost_capacity,
+                                                  migrant_capacity=migrant_capacity, ingest_capacity=ingest_capacity,
+                                                  bounds=bnds)
+        self._build(slab_count, self.bounds, max_particles_per_slab)
+
+    def _build(self, slab_count: int, bounds, max_particles_per_slab: int) -> None:
+        self.max_particles_per_slab = max_particles_per_slab
+        self.slabs = [self._make(r, bounds, max_particles_per_slab) for r in range(slab_count)]
         arr = (ctypes.c_void_p * slab_count)(*[s._h for s in self.slabs])
         self._g = ctypes.c_void_p()
         rc = lib().psim_group_create(arr, slab_count, ctypes.byref(self._g))
@@ -353,6 +383,22 @@ class SlabGroup:
 
     def upload(self, frame: FrameBuffer) -> None:
         self._check(lib().psim_group_upload_frame(self._g, frame.ptr))
+
+    def rebalance(self, max_particles_per_slab: int = 0) -> list[int]:
+        """Move the slab boundaries to where the particles are now: the latest state is
+        downloaded, the rows are cut again by psim_balance_rows, the slabs are re-created on the new rows and the
+        state goes back in -- an upload's worth of work, for between frames when the imbalance has grown. The
+        step / re-bin countdown restarts as after any upload. Returns the new boundaries."""
+        self.snapshot_async()
+        frame = self.download()
+        bounds = balance_rows(frame, self.grid_log2[1], len(self.slabs))
+        cap = max_particles_per_slab or self.max_particles_per_slab
+        count = len(self.slabs)
+        self.close()
+        self.bounds = bounds
+        self._build(count, bounds, cap)
+        self.upload(frame)
+        return bounds
 
     def set_metadata(self, metadata: np.ndarray) -> None:
         meta = np.ascontiguousarray(metadata, dtype=METADATA_DTYPE)

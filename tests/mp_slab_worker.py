@@ -27,8 +27,9 @@ def main() -> int:
     n = wl.particles
     uid = slabs.broadcast_bytes(dist, Stepper.comm_unique_id() if rank == 0 else None, 128)
     # the lattice splits evenly at first and melts across the boundaries: leave room for the imbalance
+    bounds = [int(b) for b in os.environ["PSIM_TEST_BOUNDS"].split(",")] if os.environ.get("PSIM_TEST_BOUNDS") else None
     st = Stepper(wl.grid_log2, int(0.75 * n) if world > 1 else n, device=local, slab_rank=rank, slab_count=world,
-                 ingest_capacity=n)
+                 ingest_capacity=n, bounds=bounds)
     st.comm_init(uid)
     want_mode = {"push": 2, "nccl": 1}.get(os.environ.get("PSIM_EXPECT_HALO", ""), 0)
     if rank == 0:

@@ -22,13 +22,24 @@ def _gpus() -> int:
 def test_nccl_slabs_are_bit_identical_to_single_slab(world, halo):
     """halo = push: the step kernel stores boundary rows into the neighbours' ghost rows over peer memory (CUDA IPC);
     halo = nccl: an ncclSend/ncclRecv pair per neighbour after every step (PSIM_HALO=nccl)."""
+    run_workers(world, halo)
+
+
+def test_nccl_slabs_of_unequal_heights():
+    """PsimConfig.slab_bounds across processes: slab 0 owns 640 of the 1024 cell rows, slab 1 the rest."""
+    run_workers(2, "push", bounds="0,640,1024", port=29650)
+
+
+def run_workers(world, halo, bounds=None, port=None):
     if _gpus() < world:
         pytest.skip(f"needs {world} GPUs, this box has {_gpus()}")
     env = dict(os.environ, PSIM_EXPECT_HALO=halo)
+    if bounds:
+        env["PSIM_TEST_BOUNDS"] = bounds
     if halo == "nccl":
         env["PSIM_HALO"] = "nccl"
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}",
-           "--master-addr", "127.0.0.1", "--master-port", str(29600 + world + (10 if halo == "nccl" else 0)),
+           "--master-addr", "127.0.0.1", "--master-port", str(port or 29600 + world + (10 if halo == "nccl" else 0)),
            os.path.join(REPO, "tests", "mp_slab_worker.py"), "3"]
     # own session: if a rank hangs, the whole process group is killed, never left spinning on the GPUs
     proc = subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, cwd=REPO, env=env,

@@ -15,13 +15,13 @@ from particle_simulator_b200 import FrameBuffer, io
 pytestmark = pytest.mark.gpu
 
 
-def run_both(fb: FrameBuffer, grid, slabs: int, frames: int, per_slab_capacity: int | None = None):
+def run_both(fb: FrameBuffer, grid, slabs: int, frames: int, per_slab_capacity: int | None = None, bounds=None):
     """Run `frames` frames single-slab and as a slab group; yield (single, group, the group) per frame."""
     from particle_simulator_b200.stepper import SlabGroup, Stepper
 
     n = fb.count
     cap = per_slab_capacity or n
-    with Stepper(grid, n) as st, SlabGroup(grid, slabs, cap, ingest_capacity=n) as gr:
+    with Stepper(grid, n) as st, SlabGroup(grid, slabs, cap, ingest_capacity=n, bounds=bounds) as gr:
         st.upload(fb)
         gr.upload(fb)
         assert gr.particle_count == st.particle_count
@@ -49,6 +49,56 @@ def test_group_is_bit_identical_to_single_slab(golden, scene, slabs):
         assert single.tobytes() == group.tobytes()
         stages += 1
     assert stages == 3
+
+
+@pytest.mark.parametrize("scene,bounds", [("hex2500", [0, 30, 32, 34, 64]),          # two 2-row slabs in the crystal
+                                          ("gas10k", [0, 2, 11, 40, 62, 64]),       # 5 slabs (not a power of two)
+                                          ("wall_cursor", [0, 21, 64])])
+def test_slabs_of_unequal_heights_are_bit_identical_too(golden, scene, bounds):
+    """PsimConfig.slab_bounds: every slab owns the rows it is told to."""
+    g = golden(scene)
+    meta = g["meta"][0].copy()
+    meta["steps_per_frame"] = 35
+    fb = frame_from(g["input"], meta)
+    for single, group, gr in run_both(fb, (6, 6), len(bounds) - 1, frames=3, bounds=bounds):
+        assert single.tobytes() == group.tobytes()
+        info = [s.slab_info() for s in gr.slabs]
+        assert [i["first_row"] for i in info] == bounds[:-1] and [i["rows"] for i in info] == np.diff(bounds).tolist()
+
+
+def test_balanced_boundaries_and_rebalancing_a_running_group():
+    """the clustered scene (BASELINE.json configs[4]) cut by psim_balance_rows instead of into
+    equal numbers of rows, on a fine grid (step_kernel_c with the halo pushed by the step kernel). Results stay
+    bit-identical to the single slab; the boundaries are moved again while the scene runs."""
+    from particle_simulator_b200 import workloads
+    from particle_simulator_b200.stepper import SlabGroup, Stepper, balance_rows
+
+    w = workloads.clustered_mixed((10, 10), clusters=6, side=150, gas=20000, seed=5)
+    w.frame.metadata["steps_per_frame"] = 50
+    n = w.particles
+    bounds = balance_rows(w.frame, 10, 8)
+    with Stepper(w.grid_log2, n) as st, SlabGroup(w.grid_log2, 8, n, ingest_capacity=n, bounds=bounds) as gr:
+        st.upload(w.frame)
+        gr.upload(w.frame)
+        held = np.array([s.particle_count for s in gr.slabs])
+        assert held.sum() == n and held.max() / held.mean() < 1.1, held   # equal rows: 2.4 (test_gpu_configs.py)
+        assert gr.slabs[3].tile_stats()["float_path"] == 1
+        for frame in range(3):
+            st.run_frame_async()
+            gr.run_frame_async()
+            st.sync()
+            gr.sync()
+            assert st.download().particles.tobytes() == gr.download().particles.tobytes()
+            if frame == 1:
+                # move the boundaries to where the particles are now; the single slab restarts its schedule the same
+                # way by taking its own state back in
+                new = gr.rebalance()
+                assert (np.diff(new) >= 2).all() and new[0] == 0 and new[-1] == 1024
+                st.snapshot_async()
+                st.upload(st.download())
+                held = np.array([s.particle_count for s in gr.slabs])
+                assert held.sum() == n and held.max() / held.mean() < 1.1, held
+                assert [s.slab_info()["first_row"] for s in gr.slabs] == new[:-1]
 
 
 def test_ingest_and_fine_grained_calls_match(golden):
@@ -187,6 +237,10 @@ def test_bad_slab_configurations_are_rejected():
         Stepper((6, 6), 100, slab_rank=0, slab_count=3)
     with pytest.raises(PsimError, match="slab_rank"):
         Stepper((6, 6), 100, slab_rank=2, slab_count=2)
+    for bad in ([0, 1, 64], [0, 63, 64], [0, 40, 30, 64], [2, 30, 64], [0, 30, 60]):
+        with pytest.raises(PsimError, match="slab_bounds"):
+            for r in range(len(bad) - 1):
+                Stepper((6, 6), 100, slab_rank=r, slab_count=len(bad) - 1, bounds=bad).close()
     with Stepper((6, 6), 100, slab_rank=1, slab_count=2) as st:
         fb = FrameBuffer(4)
         io.scene_hex_square(fb, 2, 2, (25e-9, 40e-9), 1.0, 5.0, 5.0, 0, seed=7)

@@ -20,6 +20,36 @@ def test_slab_rows_and_owner():
     assert slabs.slab_of(y, 4, 6).tolist() == [0, 0, 1, 3]
 
 
+def test_balance_rows_cuts_a_lopsided_scene_into_equal_shares():
+    """psim_balance_rows (host code of libpsim_b200.so, no GPU): SURVEY.md section 8e's movable slab boundaries."""
+    from particle_simulator_b200.stepper import PsimError, balance_rows
+
+    w = workloads.clustered_mixed((8, 8), clusters=4, side=30, gas=2000, seed=5)
+    p = w.frame.particles
+    equal = np.bincount(slabs.slab_of(p["y"], 8, 8), minlength=8)
+    bounds = balance_rows(w.frame, 8, 8)
+    assert bounds[0] == 0 and bounds[-1] == 256 and (np.diff(bounds) >= 2).all()
+    held = np.bincount(slabs.slab_of(p["y"], 8, 8, bounds), minlength=8)
+    assert held.sum() == len(p)
+    assert equal.max() / equal.mean() > 1.8                  # equal rows: badly balanced
+    row_max = np.bincount((p["y"] >> np.uint32(24)).astype(np.int64)).max()
+    assert held.max() - held.mean() <= row_max               # balanced to within one cell row of particles
+    assert held.max() / held.mean() < 1.25, held
+    parts = slabs.split_by_slab(p, 8, 8, bounds)
+    assert [len(q) for q in parts] == held.tolist()
+    # null records do not count; an empty scene still gives every slab its two rows
+    q = p.copy()
+    q["ty"][q["y"] < (1 << 31)] = -1
+    half = FrameBuffer(len(q), w.frame.metadata)
+    half.set_particles(q)
+    b2 = balance_rows(half, 8, 4)
+    assert b2[1] >= 128 - 2 and (np.diff(b2) >= 2).all()
+    assert balance_rows(FrameBuffer(1), 6, 32) == list(range(0, 65, 2))
+    assert balance_rows(w.frame, 8, 1) == [0, 256]
+    with pytest.raises(PsimError, match="every slab needs 2"):
+        balance_rows(w.frame, 6, 33)
+
+
 def test_split_by_slab_is_a_partition_in_input_order():
     fb = FrameBuffer(4000)
     io.scene_hex_square(fb, 50, 80, (25e-9, 25e-9), 1.0, 5.0, 5.0, 0, seed=11)
