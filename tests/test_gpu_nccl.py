@@ -26,8 +26,8 @@ def test_nccl_slabs_are_bit_identical_to_single_slab(world, halo):
 
 
 def test_nccl_slabs_of_unequal_heights():
-    """PsimConfig.slab_bounds across processes: slab 0 owns 640 of the 1024 cell rows, slab 1 the rest."""
-    run_workers(2, "push", bounds="0,640,1024", port=29650)
+    """PsimConfig.slab_bounds across processes: slab 0 owns 448 of the 1024 cell rows (38 % of the particles), slab 1 the rest."""
+    run_workers(2, "push", bounds="0,448,1024", port=29650)
 
 
 def run_workers(world, halo, bounds=None, port=None):
