@@ -55,8 +55,8 @@ def build_io(force: bool = False) -> str:
 
 def build_psim(force: bool = False, verbose: bool = False) -> str:
     src = [os.path.join(CSRC, "stepper.cu")]
-    deps = src + [os.path.join(CSRC, "step_float.cuh"), os.path.join(INCLUDE, "psim_b200.h"),
-                  os.path.join(INCLUDE, "particle_io.h")]
+    kernels = [os.path.join(CSRC, f) for f in ("device_common.cuh", "step_int.cuh", "step_float.cuh", "binning.cuh")]
+    deps = src + kernels + [os.path.join(INCLUDE, "psim_b200.h"), os.path.join(INCLUDE, "particle_io.h")]
     if force or _stale(LIB_PSIM, deps):
         cmd = [_nvcc(), *NVCC_ARCH, "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC", "-shared",
                "-I" + INCLUDE, *src, "-o", LIB_PSIM, "-ldl"]

@@ -1,0 +1,375 @@
+// binning.cuh -- the stable counting sort by cell (ingest and re-bin), the tile tables, neighbour records, snapshots, and migration between slabs.
+// Included by stepper.cu inside its anonymous namespace (one translation unit: the kernels, their parameter blocks and
+// the host code that launches them are compiled together). Not a stand-alone header.
+
+// ------------------------------------------------------------------------------------------------
+// Binning: stable counting sort by cell (count -> scan -> scatter -> order fix-up + gather).
+//
+//   key_count : key = cell(pos); rank = atomicAdd(count[key], 1)          (arbitrary rank in cell)
+//   scan      : cell_start = exclusive prefix sum of count                 (3 small kernels)
+//   scatter   : perm[cell_start[key] + rank] = candidate index
+//   gather    : slot p holds candidate c = perm[p]; its final place inside its cell is the number of
+//               cell-mates with a smaller candidate index, which makes the result the STABLE sort
+//               whatever order the atomics were served in -- the order the reference's serial
+//               append (kernel.cuh:219-229) and its (row, column, slot) pull (kernel_bucket.cuh:17-33)
+//               both produce.
+// The candidates are, in this order: wire-format records ahead of the live state (an ingested frame,
+// or the particles that migrated in from the lower slab), the live particles this stepper owns, and
+// records behind them (migrants from the upper slab) -- the order those particles have in the global
+// cell-sorted array, so that a slab-decomposed run sorts exactly like a single-slab one.
+// ------------------------------------------------------------------------------------------------
+
+struct Source {
+    const Particle* aos_lo;  // records that sort ahead of the live state (may contain nulls, ty < 0)
+    uint32_t n_lo;
+    const uint2* pos;  // the live state, particles [soa_lo, soa_lo + n_soa)
+    const float2* vel;
+    const int32_t* ty;
+    uint32_t soa_lo, n_soa;
+    const Particle* aos_hi;  // records that sort behind it
+    uint32_t n_hi;
+    uint32_t strict;  // 1: a record outside the owned rows is an error (migrants), 0: it is skipped (ingest)
+};
+
+__device__ __forceinline__ uint32_t source_count(const Source& s) { return s.n_lo + s.n_soa + s.n_hi; }
+
+// Position / velocity / label of candidate c; returns false for a null record (kernel.cuh:222).
+__device__ __forceinline__ bool source_fetch(const Source& s, uint32_t c, uint2& pos, float2& vel, int32_t& ty,
+                                             bool& is_record) {
+    const Particle* rec = nullptr;
+    if (c < s.n_lo) rec = s.aos_lo + c;
+    else if (c >= s.n_lo + s.n_soa) rec = s.aos_hi + (c - s.n_lo - s.n_soa);
+    is_record = rec != nullptr;
+    if (rec) {
+        Particle q = *rec;
+        pos = make_uint2(q.x, q.y);
+        vel = make_float2(q.vx, q.vy);
+        ty = q.ty;
+        return q.ty >= 0;
+    }
+    uint32_t i = s.soa_lo + (c - s.n_lo);
+    pos = s.pos[i];
+    vel = s.vel[i];
+    ty = s.ty[i];
+    return true;
+}
+
+// device-side error bits (PsimStepper::d_flags[0])
+constexpr uint32_t kErrMigrantOutside = 1u;   // a migrant record does not belong to this slab
+constexpr uint32_t kErrMigrantOverflow = 2u;  // more migrants than the exchange boxes hold
+constexpr uint32_t kErrMigrantTooFar = 4u;    // a particle left for a slab that is not adjacent
+
+__global__ void key_count_kernel(Source src, Grid g, uint32_t* __restrict__ cell_count, uint32_t* __restrict__ rank,
+                                 uint32_t* __restrict__ flags) {
+    uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= source_count(src)) return;
+    uint2 pos;
+    float2 vel;
+    int32_t ty;
+    bool is_record;
+    if (!source_fetch(src, c, pos, vel, ty, is_record)) return;
+    uint32_t key = cell_of(pos, g);
+    if (key >= kKeyUp) {  // outside the owned rows: filtered (ingest) or already extracted (live state)
+        if (is_record && src.strict) atomicOr(flags, kErrMigrantOutside);
+        return;
+    }
+    rank[c] = atomicAdd(&cell_count[key], 1u);
+}
+
+// PAD: scan the counts rounded up to even (pad_start of the fp32 step kernel) instead of the counts.
+template <bool PAD>
+__device__ __forceinline__ uint32_t scan_item(uint32_t v) {
+    return PAD ? (v + 1u) & ~1u : v;
+}
+
+template <bool PAD>
+__global__ void __launch_bounds__(kScanThreads) scan_reduce_kernel(const uint32_t* __restrict__ in, uint32_t count,
+                                                                   uint32_t* __restrict__ block_sum) {
+    __shared__ uint32_t warp_sum[kScanThreads / 32];
+    uint32_t base = blockIdx.x * kScanBlock + threadIdx.x * kScanItems;
+    uint32_t v = 0;
+#pragma unroll
+    for (int k = 0; k < kScanItems; ++k)
+        if (base + k < count) v += scan_item<PAD>(in[base + k]);
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xFFFFFFFFu, v, o);
+    if ((threadIdx.x & 31) == 0) warp_sum[threadIdx.x >> 5] = v;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint32_t t = 0;
+        for (int w = 0; w < kScanThreads / 32; ++w) t += warp_sum[w];
+        block_sum[blockIdx.x] = t;
+    }
+}
+
+// single block: exclusive scan of block_sum in place, total -> *total_out
+__global__ void __launch_bounds__(1024) scan_top_kernel(uint32_t* __restrict__ block_sum, uint32_t blocks,
+                                                        uint32_t* __restrict__ total_out) {
+    __shared__ uint32_t warp_sum[32];
+    __shared__ uint32_t carry;
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    for (uint32_t base = 0; base < blocks; base += 1024) {
+        uint32_t idx = base + threadIdx.x;
+        uint32_t v = idx < blocks ? block_sum[idx] : 0;
+        uint32_t incl = v;
+        for (int o = 1; o < 32; o <<= 1) {
+            uint32_t t = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+            if ((threadIdx.x & 31) >= o) incl += t;
+        }
+        if ((threadIdx.x & 31) == 31) warp_sum[threadIdx.x >> 5] = incl;
+        __syncthreads();
+        if (threadIdx.x < 32) {
+            uint32_t w = warp_sum[threadIdx.x], wi = w;
+            for (int o = 1; o < 32; o <<= 1) {
+                uint32_t t = __shfl_up_sync(0xFFFFFFFFu, wi, o);
+                if (threadIdx.x >= o) wi += t;
+            }
+            warp_sum[threadIdx.x] = wi - w;  // exclusive
+        }
+        __syncthreads();
+        uint32_t excl = carry + warp_sum[threadIdx.x >> 5] + incl - v;
+        if (idx < blocks) block_sum[idx] = excl;
+        __syncthreads();
+        if (threadIdx.x == 1023) carry = excl + v;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) *total_out = carry;
+}
+
+template <bool PAD>
+__global__ void __launch_bounds__(kScanThreads) scan_apply_kernel(const uint32_t* __restrict__ in, uint32_t count,
+                                                                  const uint32_t* __restrict__ block_offset,
+                                                                  uint32_t* __restrict__ out) {
+    __shared__ uint32_t warp_sum[kScanThreads / 32];
+    uint32_t base = blockIdx.x * kScanBlock + threadIdx.x * kScanItems;
+    uint32_t v[kScanItems];
+    uint32_t t = 0;
+#pragma unroll
+    for (int k = 0; k < kScanItems; ++k) {
+        v[k] = base + k < count ? scan_item<PAD>(in[base + k]) : 0;
+        t += v[k];
+    }
+    uint32_t incl = t;
+    for (int o = 1; o < 32; o <<= 1) {
+        uint32_t u = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+        if ((threadIdx.x & 31) >= o) incl += u;
+    }
+    if ((threadIdx.x & 31) == 31) warp_sum[threadIdx.x >> 5] = incl;
+    __syncthreads();
+    uint32_t woff = 0;
+    for (int w = 0; w < (int)(threadIdx.x >> 5); ++w) woff += warp_sum[w];
+    uint32_t run = block_offset[blockIdx.x] + woff + incl - t;
+#pragma unroll
+    for (int k = 0; k < kScanItems; ++k) {
+        if (base + k < count) out[base + k] = run;
+        run += v[k];
+    }
+}
+
+__global__ void scatter_kernel(Source src, Grid g, const uint32_t* __restrict__ cell_start,
+                               const uint32_t* __restrict__ rank, uint32_t* __restrict__ perm) {
+    uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= source_count(src)) return;
+    uint2 pos;
+    float2 vel;
+    int32_t ty;
+    bool is_record;
+    if (!source_fetch(src, c, pos, vel, ty, is_record)) return;
+    uint32_t key = cell_of(pos, g);
+    if (key >= kKeyUp) return;
+    perm[cell_start[key] + rank[c]] = c;
+}
+
+// Slots [p_lo, p_hi) of the sorted arrays are the owned rows; ghost rows are filled by the exchange.
+__global__ void gather_kernel(Source src, uint32_t p_lo, uint32_t p_hi, Grid g,
+                              const uint32_t* __restrict__ cell_start, const uint32_t* __restrict__ perm,
+                              uint2* __restrict__ pos_out, float2* __restrict__ vel_out,
+                              int32_t* __restrict__ ty_out, uint32_t* __restrict__ cell_id_out,
+                              float4* __restrict__ nbr_out, PhysF pf) {
+    uint32_t p = p_lo + blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= p_hi) return;
+    uint32_t c = perm[p];
+    uint2 pos;
+    float2 vel;
+    int32_t ty;
+    bool is_record;
+    source_fetch(src, c, pos, vel, ty, is_record);
+    uint32_t key = cell_of(pos, g);
+    uint32_t s = cell_start[key], e = cell_start[key + 1];
+    uint32_t r = 0;
+    for (uint32_t k = s; k < e; ++k) r += perm[k] < c ? 1u : 0u;
+    uint32_t dst = s + r;
+    pos_out[dst] = pos;
+    vel_out[dst] = vel;
+    ty_out[dst] = ty;
+    cell_id_out[dst] = key;
+    if (nbr_out) nbr_out[dst] = nbr_record(pos, key, g, pf);
+}
+
+// Neighbour records of particles [lo, hi) from their positions and membership cells (found in cell_start): ghost
+// rows that arrived as bare positions, or everything after the metadata changed the scale.
+__global__ void nbr_rebuild_kernel(const uint2* __restrict__ pos, const uint32_t* __restrict__ cell_start, Grid g,
+                                   PhysF pf, uint32_t lo, uint32_t hi, float4* __restrict__ nbr) {
+    const uint32_t i = lo + blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= hi) return;
+    nbr[i] = nbr_record(pos[i], (uint32_t)last_le(cell_start, (int)g.cells, i), g, pf);
+}
+
+// The few numbers the host needs after a binning: where the owned rows and their two boundary rows
+// start and end in the sorted arrays. out[0] = own_lo, [1] = end of the first owned row,
+// [2] = start of the last owned row, [3] = own_hi, [4] = total (with ghost rows), [5] = error flags,
+// [6] = tiles of step_kernel_c, [7] = its tiles of the first owned row, [8] = its first tile of the last owned row.
+// The start of the upper ghost row is also published in the slab's HaloHeader for the lower neighbour's pushes.
+constexpr uint32_t kErrHaloTimeout = 8u;  // a step waited 20 s for a neighbour's halo
+__global__ void slab_counts_kernel(const uint32_t* __restrict__ cell_start, Grid g, const uint32_t* __restrict__ flags,
+                                   const uint32_t* __restrict__ couple_tiles, const uint32_t* __restrict__ tile_base,
+                                   HaloHeader* __restrict__ hdr, uint32_t* __restrict__ out) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    out[6] = couple_tiles ? *couple_tiles : 0u;  // tiles of step_kernel_c (step_float.cuh)
+    out[7] = tile_base ? tile_base[1] : 0u;
+    out[8] = tile_base ? tile_base[g.own_rows - 1] : 0u;
+    if (hdr) {
+        hdr->own_hi = cell_start[(g.own_row0 + g.own_rows) * g.bx];
+        out[5] = flags[0] | (hdr->error ? kErrHaloTimeout : 0u);
+        out[0] = cell_start[g.own_row0 * g.bx];
+        out[1] = cell_start[(g.own_row0 + 1) * g.bx];
+        out[2] = cell_start[(g.own_row0 + g.own_rows - 1) * g.bx];
+        out[3] = hdr->own_hi;
+        out[4] = cell_start[g.cells];
+        return;
+    }
+    out[0] = cell_start[g.own_row0 * g.bx];
+    out[1] = cell_start[(g.own_row0 + 1) * g.bx];
+    out[2] = cell_start[(g.own_row0 + g.own_rows - 1) * g.bx];
+    out[3] = cell_start[(g.own_row0 + g.own_rows) * g.bx];
+    out[4] = cell_start[g.cells];
+    out[5] = flags[0];
+}
+
+// Cell ids of a ghost row: its particles arrive as bare positions; the ids are needed by nobody (ghosts
+// are never stepped) -- but the row's cell_start entries are, and those come from the scan.
+
+// One descriptor per tile of kTile consecutive OWNED particles: the cell range of the tile, and for each
+// of the three stencil rows the (16-byte aligned) slices of cell_start and of the position array that its
+// CTA stages in shared memory (see step_kernel).
+__global__ void tile_desc_kernel(const uint32_t* __restrict__ cell_start, Grid g, uint32_t own_lo, uint32_t own_hi,
+                                 TileDesc* __restrict__ tiles) {
+    uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+    uint32_t ntiles = (own_hi - own_lo + kTile - 1) / kTile;
+    if (b >= ntiles) return;
+    uint32_t i0 = own_lo + b * kTile, i1 = min(own_hi, i0 + kTile) - 1;
+    TileDesc t;
+    t.first = (uint32_t)last_le(cell_start, (int)g.cells, i0);
+    t.last = (uint32_t)last_le(cell_start, (int)g.cells, i1);
+    t._pad = 0;
+    bool fits = true;
+    for (int d = 0; d < 3; ++d) {
+        long long shift = (long long)(d - 1) * (long long)g.bx;
+        long long lo = max((long long)t.first - 1 + shift, 0ll);
+        long long hi = min((long long)t.last + 1 + shift, (long long)g.cells - 1);
+        if (hi < lo) {  // the whole row lies outside the grid
+            t.cs_lo[d] = t.cs_cnt[d] = t.p_lo[d] = t.p_cnt[d] = 0;
+            continue;
+        }
+        uint32_t cs_lo = (uint32_t)lo & ~3u;
+        uint32_t cs_cnt = (((uint32_t)hi + 2 - cs_lo) + 3u) & ~3u;  // entries lo .. hi+1
+        uint32_t p_lo = cell_start[lo] & ~1u;
+        uint32_t p_cnt = ((cell_start[hi + 1] - p_lo) + 1u) & ~1u;
+        t.cs_lo[d] = cs_lo;
+        t.cs_cnt[d] = cs_cnt;
+        t.p_lo[d] = p_lo;
+        t.p_cnt[d] = p_cnt;
+        fits = fits && cs_cnt <= (uint32_t)kCsCap && p_cnt <= (uint32_t)kPosCap;
+    }
+    t.fits = fits ? 1u : 0u;
+    tiles[b] = t;
+}
+
+// snapshot: pack the owned particles back into wire-format records (particle.rs:10-18)
+// With stride > 1 only every stride-th particle of the (cell-sorted, hence spatially coherent) state is packed: a
+// decimated snapshot for display, 1/stride of the bytes to copy out and send.
+__global__ void pack_kernel(const uint2* __restrict__ pos, const float2* __restrict__ vel,
+                            const int32_t* __restrict__ ty, uint32_t lo, uint32_t hi, uint32_t stride,
+                            Particle* __restrict__ out) {
+    const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint64_t i64 = (uint64_t)lo + (uint64_t)k * stride;
+    if (i64 >= hi) return;
+    const uint32_t i = (uint32_t)i64;
+    uint2 p = pos[i];
+    float2 v = vel[i];
+    Particle q;
+    q.x = p.x;
+    q.y = p.y;
+    q.vx = v.x;
+    q.vy = v.y;
+    q.ty = ty[i];
+    out[k] = q;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Migration between slabs at re-bin time: owned particles whose position left the owned rows are
+// collected (atomics, arbitrary order), then written to a fixed-size box in ascending index order
+// (= the order they have in the global sorted array) for the neighbour to merge.
+// ------------------------------------------------------------------------------------------------
+
+struct MigrantBoxHeader {
+    uint32_t count;
+    uint32_t _pad[3];
+};
+
+__global__ void migrant_extract_kernel(const uint2* __restrict__ pos, uint32_t own_lo, uint32_t own_hi, Grid g,
+                                       uint32_t box_capacity, uint32_t* __restrict__ counters,
+                                       uint32_t* __restrict__ idx_down, uint32_t* __restrict__ idx_up,
+                                       uint32_t* __restrict__ flags) {
+    uint32_t i = own_lo + blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= own_hi) return;
+    uint2 p = pos[i];
+    uint32_t key = cell_of(p, g);
+    if (key < kKeyUp) return;
+    int32_t row = (int32_t)(p.y >> g.sy) - g.row_offset;
+    // anything beyond the adjacent slabs cannot be delivered
+    if (row < (int32_t)g.own_row0 - (int32_t)g.rows_below || row >= (int32_t)(g.own_row0 + g.own_rows + g.rows_above))
+        atomicOr(flags, kErrMigrantTooFar);
+    uint32_t dir = key == kKeyDown ? 0u : 1u;
+    uint32_t slot = atomicAdd(&counters[dir], 1u);
+    if (slot >= box_capacity) {
+        atomicOr(flags, kErrMigrantOverflow);
+        return;
+    }
+    (dir == 0 ? idx_down : idx_up)[slot] = i;
+}
+
+__global__ void migrant_pack_kernel(const uint2* __restrict__ pos, const float2* __restrict__ vel,
+                                    const int32_t* __restrict__ ty, const uint32_t* __restrict__ counter,
+                                    const uint32_t* __restrict__ idx, uint32_t box_capacity,
+                                    unsigned char* __restrict__ box) {
+    uint32_t count = min(*counter, box_capacity);
+    MigrantBoxHeader* header = reinterpret_cast<MigrantBoxHeader*>(box);
+    Particle* rec = reinterpret_cast<Particle*>(box + sizeof(MigrantBoxHeader));
+    uint32_t e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e == 0) {
+        header->count = count;
+        header->_pad[0] = header->_pad[1] = header->_pad[2] = 0;
+    }
+    if (e >= box_capacity) return;
+    if (e >= count) {  // the rest of the box is null records (ty < 0): the receiver scans the whole box
+        Particle q;
+        q.x = q.y = 0;
+        q.vx = q.vy = 0.f;
+        q.ty = -1;
+        rec[e] = q;
+        return;
+    }
+    uint32_t i = idx[e];
+    uint32_t r = 0;
+    for (uint32_t k = 0; k < count; ++k) r += idx[k] < i ? 1u : 0u;
+    Particle q;
+    uint2 p = pos[i];
+    float2 v = vel[i];
+    q.x = p.x;
+    q.y = p.y;
+    q.vx = v.x;
+    q.vy = v.y;
+    q.ty = ty[i];
+    rec[r] = q;
+}

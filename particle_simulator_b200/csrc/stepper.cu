@@ -17,6 +17,9 @@
 // Membership is by the LAST binning, exactly like the reference's slot array: between re-bins a
 // particle keeps its index and its cell even if it has drifted out of it (kernel_bucket.cuh:71-91).
 //
+// One translation unit: the device code lives in device_common.cuh (parameter blocks, pair arithmetic), step_int.cuh
+// (halo protocol, epilogue, step_kernel, all-pairs), step_float.cuh (step_kernel_c, couples and tiles) and binning.cuh
+// (counting sort, neighbour records, snapshots, migration); this file holds the host side and the C API.
 // There is no CPU path in this file and nothing here includes or links oracle/.
 #include <cuda_runtime.h>
 #include <dlfcn.h>
@@ -35,994 +38,10 @@
 
 namespace {
 
-// ------------------------------------------------------------------------------------------------
-// Kernel parameter blocks
-// ------------------------------------------------------------------------------------------------
-
-constexpr int kTile = 128;        // particles per CTA of the step kernel (= threads per CTA)
-constexpr int kCsCap = 288;       // cell_start entries staged per stencil row (multiple of 4)
-constexpr int kPosCap = 640;      // neighbour positions staged per stencil row (multiple of 2)
-constexpr int kScanItems = 8;     // cells per thread in the scan kernels
-constexpr int kScanThreads = 256;
-constexpr int kScanBlock = kScanItems * kScanThreads;
-constexpr int kPadCells = 8;      // readable slack after cell_start[cells] for 16-byte bulk copies
-constexpr int kPadParticles = 4;  // readable slack after pos[n] for 16-byte bulk copies
-
-struct Grid {
-    uint32_t lx;         // log2 cells in x
-    uint32_t bx;         // cells in x
-    uint32_t by;         // LOCAL cell rows held by this stepper (owned rows + ghost rows)
-    uint32_t cells;      // bx * by (local)
-    uint32_t sx, sy;     // 32 - log2(cells in x / GLOBAL cells in y): fixed-point coordinate -> global cell
-    int32_t row_offset;  // local row = global row - row_offset
-    uint32_t own_row0;   // first owned local row (1 when there is a lower ghost row, else 0)
-    uint32_t own_rows;   // owned rows
-    uint32_t rows_below, rows_above;  // rows the adjacent slabs own (0: no such slab): how far a migrant can be delivered
-};
-
-// Where a position falls relative to the rows this stepper owns.
-constexpr uint32_t kKeyDown = 0xFFFFFFFEu;  // below the slab: migrates to the lower neighbour
-constexpr uint32_t kKeyUp = 0xFFFFFFFDu;    // above the slab: migrates to the upper neighbour
-
-// How the non-integer part of the repulsive exponent is evaluated (see pair2 below).
-enum FracMode { kFracNone = 0, kFracPoly = 1, kFracEx2 = 2 };
-
-// Everything a step needs from FrameMetadata, pre-digested on the host once per metadata change
-// (the reference rebuilds ParticleParams, including a powf, in every thread of every step:
-// kernel_bucket.cuh:52, particle.cuh:53-55).
-//
-// Pair force in the units the kernel works in.  With q = sigma^2 / r^2:
-//   F_vec = C eps (m (s/r)^m - n (s/r)^n) / r^2 * r_vec                      (particle.cuh:63-66,97-103)
-//         = (C eps m / sigma^2) * (q^(m/2+1) - (n/m) q^(n/2+1)) * r_vec
-// r_vec is kept in raw fixed-point x units (dx, dy * yscale), so
-//   F_vec = pair_scale * sum_j g_j * (dx, dy')      with pair_scale = C eps m kx / sigma^2.
-struct Phys {
-    float inv_c2;        // kx^2 / sigma^2: (raw x units)^2 -> r^2 / sigma^2
-    float yscale;        // ky / kx (1 for square cells): raw y units -> raw x units
-    float nm;            // n / m
-    float fn, fm;        // exponents n/2+1 = kn + fn, m/2+1 = km + fm  (|fn|, |fm| <= 0.5)
-    int kn, km;
-    float c1, c2, c3;    // 2^z ~ 1 + z (c1 + z (c2 + z c3)) on the z range of kFracPoly
-    float pair_scale;    // scaled pair sum -> newtons (x), see above
-    float pair_scale_y;  // same for y: pair_scale (dy' is already in x units)
-    float wall_scale;    // C * eps * m
-    float sigma;
-    float inv_mass;
-    float dt;
-    float kx, ky;        // box / 2^32: fixed-point units -> metres
-    float ux, uy;        // dt * 2^32 / box: velocity -> fixed-point displacement per step
-    float cursor_x, cursor_y, cursor_r2;  // cursor_r2 = cursor_size^2 / 4
-    int wall_m6;         // m == 6: wall term by multiplication
-    int cursor_on;       // the cursor can reach a particle of the box at all
-    float m;
-};
-
-// One tile of kTile consecutive particles: what its CTA stages in shared memory. Written at re-bin
-// time (tile_desc_kernel), read by every step until the next re-bin.  64 bytes.
-struct __align__(16) TileDesc {
-    uint32_t fits;       // 1: the three stencil rows fit the staging buffers
-    uint32_t first;      // first / last cell touched by the tile's own particles
-    uint32_t last;
-    uint32_t _pad;
-    uint32_t cs_lo[3];   // first cell_start entry staged per row (multiple of 4)
-    uint32_t cs_cnt[3];  // entries staged per row (multiple of 4; 0: row outside the grid)
-    uint32_t p_lo[3];    // first particle staged per row (even)
-    uint32_t p_cnt[3];   // particles staged per row (even)
-};
-static_assert(sizeof(TileDesc) == 64, "TileDesc is read as four 16-byte words");
-
-// ------------------------------------------------------------------------------------------------
-// Device helpers
-// ------------------------------------------------------------------------------------------------
-
-__device__ __forceinline__ float fast_rcp(float x) {
-    float r;
-    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
-    return r;
-}
-__device__ __forceinline__ float fast_lg2(float x) {
-    float r;
-    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
-    return r;
-}
-__device__ __forceinline__ float fast_ex2(float x) {
-    float r;
-    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
-    return r;
-}
-
-__device__ __forceinline__ float2 splat(float v) { return make_float2(v, v); }
-
-__device__ __forceinline__ float2 powi2(float2 b, int k) {  // k is uniform across the grid
-    float2 r = splat(1.f);
-    while (k) {
-        if (k & 1) r = __fmul2_rn(r, b);
-        b = __fmul2_rn(b, b);
-        k >>= 1;
-    }
-    return r;
-}
-
-// Local cell of a position (kernel.cuh:224-226 with the slab's row offset), or kKeyDown / kKeyUp when
-// the position lies outside the owned rows. With a single slab every position is inside.
-__device__ __forceinline__ uint32_t cell_of(uint2 p, const Grid& g) {
-    int32_t row = (int32_t)(p.y >> g.sy) - g.row_offset;
-    if (row < (int32_t)g.own_row0) return kKeyDown;
-    if (row >= (int32_t)(g.own_row0 + g.own_rows)) return kKeyUp;
-    return (p.x >> g.sx) + ((uint32_t)row << g.lx);
-}
-
-// mbarrier + 1-D bulk copy (TMA) wrappers: global -> shared::cta, completion counted in bytes.
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-}
-__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void bulk_copy_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                     smem_u32(dst)),
-                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
-                 : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-    asm volatile(
-        "{\n"
-        ".reg .pred P1;\n"
-        "LAB_WAIT:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
-        "@P1 bra DONE;\n"
-        "bra LAB_WAIT;\n"
-        "DONE:\n"
-        "}" ::"r"(smem_u32(bar)),
-        "r"(parity)
-        : "memory");
-}
-
-// ------------------------------------------------------------------------------------------------
-// Two pairs at a time, on the packed fp32x2 pipe (FMUL2 / FFMA2, new on sm_100): the separation
-// i -> j (f_dist, particle.cuh:41-47: exact u32 difference, one int -> float conversion) and the Mie
-// force written on r^2 so that no square root is needed (see Phys).  With r2 = r^2 / sigma^2 and
-// q = 1 / r2, per pair   g = q^km - (n/m) q^kn * q^fn   (km = 4 for m = 6).
-// q^fn, the non-integer sliver of the repulsive exponent (n = 14.08 -> kn = 8, fn = 0.04), is
-// 2^(-fn log2 r2): MUFU.LG2, then either a host-fitted cubic in z = -fn log2 r2 (kFracPoly: |z| is
-// small, the cubic is exact to ~1e-8 where the term matters) or MUFU.EX2 (kFracEx2).  Integer powers
-// are products; each term keeps a relative error of a few 1e-7, no worse than the reference's own
-// fp32 `powf(sigma / len, n)`.  MUFU runs at 16 lanes/clk/SM (measured, tools/microbench.cu), so the
-// two MUFU ops per pair (RCP, LG2) are what bounds this loop, with issue slots a close second.
-// MASK1: the second pair of the packed couple does not exist (odd tail) and contributes exactly 0.
-// CLAMP: the window may contain i itself (own row): r2 is clamped away from 0 so that g stays
-// finite and the zero separation gives an exact 0 (kernel_bucket.cuh:85 skips j == i).
-// ------------------------------------------------------------------------------------------------
-// f_dist for any two particles of the box (particle.cuh:41-47): the unsigned difference can exceed 2^31.
-__device__ __forceinline__ float wide_diff(uint32_t b, uint32_t a) {
-    return a < b ? __uint2float_rn(b - a) : -__uint2float_rn(a - b);
-}
-
-// WIDE: the two particles may be further apart than half the box (all-pairs mode); inside a 3x3 stencil of a
-// grid of >= 8 cells per axis the wrapping signed difference is the separation.
-template <int KN, int FRAC, bool ANISO, bool MASK1, bool CLAMP, bool WIDE = false>
-__device__ __forceinline__ void pair2(uint2 pi, uint2 pj0, uint2 pj1, const Phys& ph, float2& gx, float2& gy) {
-    float2 x, y;
-    if (WIDE) {
-        x = make_float2(wide_diff(pj0.x, pi.x), wide_diff(pj1.x, pi.x));
-        y = make_float2(wide_diff(pj0.y, pi.y), wide_diff(pj1.y, pi.y));
-    } else {
-        x = make_float2(__int2float_rn((int)(pj0.x - pi.x)), __int2float_rn((int)(pj1.x - pi.x)));
-        y = make_float2(__int2float_rn((int)(pj0.y - pi.y)), __int2float_rn((int)(pj1.y - pi.y)));
-    }
-    if (ANISO) y = __fmul2_rn(y, splat(ph.yscale));
-    float2 r2 = __ffma2_rn(y, y, __fmul2_rn(x, x));
-    r2 = __fmul2_rn(r2, splat(ph.inv_c2));
-    if (MASK1) r2.y = 1e12f;
-    if (CLAMP) {
-        r2.x = fmaxf(r2.x, 1e-2f);
-        r2.y = fmaxf(r2.y, 1e-2f);
-    }
-    float2 q = make_float2(fast_rcp(r2.x), fast_rcp(r2.y));
-    float2 q2 = __fmul2_rn(q, q);
-    float2 q4 = __fmul2_rn(q2, q2);
-    float2 pm, pn;
-    if (KN > 0) {  // m = 6 (q^4) and a compile-time integer part of n/2 + 1
-        pm = q4;
-        if (KN == 5) pn = __fmul2_rn(q4, q);
-        else if (KN == 6) pn = __fmul2_rn(q4, q2);
-        else if (KN == 7) pn = __fmul2_rn(__fmul2_rn(q4, q2), q);
-        else if (KN == 8) pn = __fmul2_rn(q4, q4);
-        else if (KN == 9) pn = __fmul2_rn(__fmul2_rn(q4, q4), q);
-        else pn = __fmul2_rn(__fmul2_rn(q4, q4), q2);
-    } else {  // any exponents: run-time integer parts
-        pm = powi2(q, ph.km);
-        pn = powi2(q, ph.kn);
-    }
-    if (FRAC != kFracNone) {
-        float2 l = make_float2(fast_lg2(r2.x), fast_lg2(r2.y));
-        float2 z = __fmul2_rn(l, splat(-ph.fn));
-        float2 e;
-        if (FRAC == kFracPoly) {
-            e = __ffma2_rn(z, splat(ph.c3), splat(ph.c2));
-            e = __ffma2_rn(z, e, splat(ph.c1));
-            e = __ffma2_rn(z, e, splat(1.f));
-        } else {
-            e = make_float2(fast_ex2(z.x), fast_ex2(z.y));
-        }
-        pn = __fmul2_rn(pn, e);
-        if (KN == 0 && ph.fm != 0.f) {
-            float2 zm = __fmul2_rn(l, splat(-ph.fm));
-            pm = __fmul2_rn(pm, make_float2(fast_ex2(zm.x), fast_ex2(zm.y)));
-        }
-    }
-    float2 g = __ffma2_rn(pn, splat(-ph.nm), pm);
-    gx = __ffma2_rn(g, x, gx);
-    gy = __ffma2_rn(g, y, gy);
-}
-
-// All of one window [0, count) of staged neighbours, two at a time, in ascending index order.
-// CG: the window lies in global memory; loads go to L2 (a ghost row is written by the neighbour slab while
-// this kernel runs, and another tile on this SM may have pulled a stale copy of its sector into L1).
-template <bool CG>
-__device__ __forceinline__ uint2 load_pos(const uint2* p) {
-    return CG ? __ldcg(p) : *p;
-}
-
-template <int KN, int FRAC, bool ANISO, bool CLAMP, bool CG>
-__device__ __forceinline__ void window_accumulate(const uint2* __restrict__ pj, int count, uint2 pi, const Phys& ph,
-                                                  float2& gx, float2& gy) {
-    int k = 0;
-#pragma unroll 2
-    for (; k + 1 < count; k += 2)
-        pair2<KN, FRAC, ANISO, false, CLAMP>(pi, load_pos<CG>(pj + k), load_pos<CG>(pj + k + 1), ph, gx, gy);
-    if (k < count) pair2<KN, FRAC, ANISO, true, CLAMP>(pi, load_pos<CG>(pj + k), pi, ph, gx, gy);
-}
-
-// Repulsive wall term C eps m (sigma/d)^m / d (particle.cuh:68-71).
-// M6: m == 6 is known at compile time (every kernel variant with compile-time powers): no predicated-off MUFU pair.
-template <bool M6>
-__device__ __forceinline__ float wall_term(float d, const Phys& ph) {
-    float inv_d = fast_rcp(d);
-    float q = ph.sigma * inv_d;
-    float pw;
-    if (M6 || ph.wall_m6) {
-        float q2 = q * q;
-        pw = q2 * q2 * q2;
-    } else {
-        pw = fast_ex2(ph.m * fast_lg2(q));
-    }
-    return ph.wall_scale * pw * inv_d;
-}
-
-// Cursor + wall forces on one particle (kernel_bucket.cuh:54-69, particle.cuh:125-144).
-template <bool M6>
-__device__ __forceinline__ float2 field_force(uint2 p, const Phys& ph) {
-    const float inv32 = 1.f / 4294967296.f;
-    float2 f = make_float2(0.f, 0.f);
-    if (ph.cursor_on) {  // uniform: the editor parks the cursor at (-1, -1), out of reach of every particle
-        float dx = ph.cursor_x - __uint2float_rn(p.x) * inv32;
-        float dy = ph.cursor_y - __uint2float_rn(p.y) * inv32;
-        float sq = dx * dx + dy * dy;
-        if (sq < ph.cursor_r2) {
-            float c = 8e-12f * fast_rcp(sq + 1.f);
-            f.x = dx > 0 ? -c : c;
-            f.y = dy > 0 ? -c : c;
-        }
-    }
-    if (p.x < 0xFFFFFFFFu / 2) f.x += wall_term<M6>(__uint2float_rn(p.x) * ph.kx, ph);
-    else f.x -= wall_term<M6>(__uint2float_rn(0xFFFFFFFFu - p.x) * ph.kx, ph);
-    if (p.y < 0xFFFFFFFFu / 2) f.y += wall_term<M6>(__uint2float_rn(p.y) * ph.ky, ph);
-    else f.y -= wall_term<M6>(__uint2float_rn(0xFFFFFFFFu - p.y) * ph.ky, ph);
-    return f;
-}
-
-// Leapfrog kick + drift on half-step velocities with wrapping fixed-point positions
-// (f_apply_force, particle.cuh:105-123): v += F/m dt; x += round(v dt / box * 2^32) (wrapping).
-// The reference's divisions by the constants mass and box are multiplications by their
-// reciprocals here (a 1-ulp difference, far inside the 1e-5 tolerance).
-__device__ __forceinline__ void integrate(uint2 p, float2 v, float2 f, const Phys& ph, uint2& p_out, float2& v_out) {
-    v_out.x = fmaf(f.x * ph.inv_mass, ph.dt, v.x);
-    v_out.y = fmaf(f.y * ph.inv_mass, ph.dt, v.y);
-    p_out.x = p.x + (uint32_t)(long long)roundf(v_out.x * ph.ux);
-    p_out.y = p.y + (uint32_t)(long long)roundf(v_out.y * ph.uy);
-}
-
-// largest c in [0, count) with a[c] <= i, given a[0] <= i  (a is non-decreasing)
-__device__ __forceinline__ int last_le(const uint32_t* a, int count, uint32_t i) {
-    int lo = 0, hi = count;  // invariant: a[lo] <= i, (hi == count or a[hi] > i)
-    while (hi - lo > 1) {
-        int mid = (lo + hi) >> 1;
-        if (a[mid] <= i) lo = mid;
-        else hi = mid;
-    }
-    return lo;
-}
-
-// ------------------------------------------------------------------------------------------------
-// The step kernel: force over the 3x3 cell stencil + kick + drift, one HBM round trip of the state.
-//
-// CTA b owns particles [b*kTile, (b+1)*kTile). Because the arrays are cell-sorted and cells are
-// row-major, everything those particles interact with lies in three contiguous index ranges, one
-// per stencil row: cells [first-1, last+1] shifted by -BX, 0, +BX. One thread reads the tile's
-// descriptor and issues up to six 1-D bulk copies (TMA, cp.async.bulk -> mbarrier) that stage the
-// cell_start entries and the positions of those ranges in shared memory; meanwhile every thread
-// loads its own particle.  Then every thread walks its own three windows (cells cx-1..cx+1 of rows
-// cy-1..cy+1, clipped at the grid edge exactly like kernel_bucket.cuh:74-77) in ascending index
-// order, the (row, column, slot) order of the reference's loop.
-// Tiles whose stencil does not fit the staging buffers (very sparse or very clustered spots) run
-// the same code with the pointers aimed at global memory instead.
-// ------------------------------------------------------------------------------------------------
-
-// ------------------------------------------------------------------------------------------------
-// Halo exchange inside the step kernel (slab decomposition).
-//
-// Each slab keeps one ghost row of each neighbour. Instead of a send/recv after every step, the threads
-// that step a particle of a boundary row store its new position twice: in the slab's own array and, through
-// peer-mapped memory (NVLink P2P: CUDA IPC between processes, plain pointers inside one process), in the
-// neighbour's ghost row of the buffer the neighbour's NEXT step reads. Synchronisation is one epoch word
-// per direction in the receiver's HaloHeader:
-//   * the thread that pushes the last particle of a boundary row publishes this step's epoch
-//     (__threadfence_system + store to the neighbour's header);
-//   * only the CTAs that read a ghost row (the tiles of the first / last owned row -- the same CTAs that
-//     produce the outgoing halo) wait, before staging, until the neighbour has published the previous
-//     step's epoch. Interior tiles never wait, so the transfer overlaps the interior's pair loops.
-// That wait also covers the write-after-read hazard: a neighbour publishes epoch k only after ITS
-// boundary tiles of step k have finished, i.e. have finished reading the ghost rows step k+1 overwrites.
-// Boundary tiles come first / last in the grid, so their halo is on the wire while the interior computes.
-// ------------------------------------------------------------------------------------------------
-// Constants of the fp32-offset step kernel (step_float.cuh) and of the neighbour records it reads.
-struct PhysF {
-    float sx, sy;          // fixed-point units -> scaled units (sx a power of two; sy = sx * ky/kx, also one)
-    float zone_shift;      // zone stride * cell width * sx: distance between the even-zone and odd-zone origins
-    float row_shift;       // cell height * sy: distance between the centres of two adjacent cell rows
-    float d0, d1, d2, d3;  // -(n/m) f^(-2(kn-km)) q^fn as a cubic in l = log2(scaled r^2)  (d0 alone if fn == 0)
-    float pair_scale;      // scaled pair sum -> newtons
-    uint32_t zl;           // log2 of the zone stride in cell columns
-    uint32_t half_span;    // (2^zl + 2) cells / 2 in fixed-point units: centre of a zone's used span
-    uint32_t sxbits;       // 32 - LX
-};
-
-struct HaloHeader {     // one per slab, in device memory its two neighbours can reach
-    uint32_t flags[2];  // [0]: last epoch published by the lower neighbour, [1]: by the upper one
-    uint32_t done[2];   // boundary particles pushed so far in the running step, per side
-    uint32_t own_hi;    // where this slab's upper ghost row starts (written at every binning)
-    uint32_t error;     // sticky: a wait timed out (the neighbour died); waits stop blocking
-    uint32_t _pad[2];
-};
-
-struct HaloArgs {
-    uint2* peer_out[2];       // the neighbour's position buffer this step writes ([0] lower, [1] upper); null: none
-    float4* peer_nbr_out[2];  // ... and its neighbour-record buffer (fine grids), or null
-    HaloHeader* peer_hdr[2];
-    HaloHeader* hdr;
-    uint32_t lo_end, hi_start;    // [own_lo, lo_end) goes to the lower neighbour, [hi_start, own_hi) to the upper one
-    uint32_t lo_tiles, hi_tile0;  // the tiles that hold (and read the ghost row next to) them: [0, lo_tiles), [hi_tile0, ..)
-    uint32_t wait_epoch[2];       // 0: the ghost row is already in place (a binning delivered it)
-    uint32_t pub_epoch;
-};
-
-constexpr unsigned long long kHaloTimeoutNs = 20ull * 1000 * 1000 * 1000;
-
-__device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
-    uint32_t v;
-    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-    return v;
-}
-__device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v) {
-    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
-}
-__device__ __forceinline__ unsigned long long global_timer_ns() {
-    unsigned long long t;
-    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-    return t;
-}
-
-struct StepArgs {
-    const uint2* __restrict__ pos_in;
-    uint2* __restrict__ pos_out;
-    float2* __restrict__ vel;
-    const uint32_t* __restrict__ cell_id;
-    const uint32_t* __restrict__ cell_start;
-    const TileDesc* __restrict__ tiles;
-    uint32_t own_lo, own_hi;  // the particles this stepper steps: [own_lo, own_hi) (ghost rows lie outside)
-    Grid g;
-    Phys ph;
-    uint32_t push;  // 1: boundary rows are pushed into the neighbours' ghost rows by this kernel (HaloArgs)
-    HaloArgs h;
-    // fine grids: every particle also has a NEIGHBOUR RECORD (x_even, y, x_odd, y): its position as exact scaled fp32
-    // offsets from the centres of its membership cell's even / odd zone and of its membership row (step_float.cuh).
-    // A step reads nbr_in (staged by TMA, no conversion) and writes nbr_out for the next one. Null on coarse grids.
-    const float4* __restrict__ nbr_in;
-    float4* __restrict__ nbr_out;
-    PhysF pf;
-};
-
-// The neighbour record of a particle at `p` whose membership cell is `cell` (local numbering).
-__device__ __forceinline__ float4 nbr_record(uint2 p, uint32_t cell, const Grid& g, const PhysF& pf) {
-    const uint32_t cx = cell & (g.bx - 1);
-    const long long row = (long long)(cell >> g.lx) + g.row_offset;              // global cell row
-    const uint32_t yc = (uint32_t)((2ll * row + 1) << (g.sy - 1));               // centre of that row
-    const uint32_t zq = cx >> pf.zl;
-    const uint32_t xo0 = (((zq & ~1u) << pf.zl) << pf.sxbits) + pf.half_span;    // centre of the even zone's span
-    const float xe = __int2float_rn((int)(p.x - xo0)) * pf.sx;
-    const float y = __int2float_rn((int)(p.y - yc)) * pf.sy;
-    return make_float4(xe, y, xe + ((zq & 1u) ? -pf.zone_shift : pf.zone_shift), y);
-}
-
-// Before a tile that reads a ghost row stages anything: wait for the neighbour's previous step (one thread).
-__device__ __forceinline__ void halo_wait(const StepArgs& a, uint32_t tile) {
-    const HaloArgs& h = a.h;
-#pragma unroll
-    for (int side = 0; side < 2; ++side) {
-        const bool reads_ghost = side == 0 ? tile < h.lo_tiles : tile >= h.hi_tile0;
-        if (!h.peer_out[side] || !h.wait_epoch[side] || !reads_ghost) continue;
-        if (ld_acquire_sys(&h.hdr->error)) continue;
-        const unsigned long long t0 = global_timer_ns();
-        while ((int32_t)(ld_acquire_sys(&h.hdr->flags[side]) - h.wait_epoch[side]) < 0) {
-            if (global_timer_ns() - t0 > kHaloTimeoutNs) {
-                st_release_sys(&h.hdr->error, 1u);
-                break;
-            }
-        }
-    }
-}
-
-__device__ __forceinline__ void halo_publish(const HaloArgs& h, int side) {
-    h.hdr->done[side] = 0;  // for the next step (its launch is ordered after this kernel)
-    __threadfence_system();
-    st_release_sys(&h.peer_hdr[side]->flags[side ^ 1], h.pub_epoch);
-}
-
-// A boundary row without particles has nobody to publish its epoch: the first thread of the grid does.
-__device__ __forceinline__ void halo_publish_empty(const StepArgs& a) {
-    const HaloArgs& h = a.h;
-    if (h.peer_out[0] && h.lo_end == a.own_lo) halo_publish(h, 0);
-    if (h.peer_out[1] && h.hi_start == a.own_hi) halo_publish(h, 1);
-}
-
-// The new position of boundary-row particle i also goes into the neighbour's ghost row.
-__device__ __forceinline__ void halo_push(const StepArgs& a, uint32_t i, uint2 po, float4 nb) {
-    const HaloArgs& h = a.h;
-    if (h.peer_out[0] && i < h.lo_end) {
-        const uint32_t base = ld_acquire_sys(&h.peer_hdr[0]->own_hi);  // the lower slab's upper ghost row
-        h.peer_out[0][base + (i - a.own_lo)] = po;
-        if (h.peer_nbr_out[0]) h.peer_nbr_out[0][base + (i - a.own_lo)] = nb;
-        __threadfence_system();
-        if (atomicAdd(&h.hdr->done[0], 1u) + 1u == h.lo_end - a.own_lo) halo_publish(h, 0);
-    }
-    if (h.peer_out[1] && i >= h.hi_start) {
-        h.peer_out[1][i - h.hi_start] = po;  // the upper slab's lower ghost row starts at 0
-        if (h.peer_nbr_out[1]) h.peer_nbr_out[1][i - h.hi_start] = nb;
-        __threadfence_system();
-        if (atomicAdd(&h.hdr->done[1], 1u) + 1u == a.own_hi - h.hi_start) halo_publish(h, 1);
-    }
-}
-
-// Which tile the b-th CTA of the grid steps. With a pushed halo the tiles of BOTH boundary rows come first (the first
-// owned row's, then the last owned row's, then the interior in order): the halo is on the wire, fenced and published
-// while the interior computes, and no neighbour ever finds a flag late because its producer ran at the grid's tail.
-__device__ __forceinline__ uint32_t halo_tile_order(const StepArgs& a, uint32_t b, uint32_t tiles) {
-    if (!a.push) return b;
-    const uint32_t lo = a.h.lo_tiles, hi0 = max(a.h.hi_tile0, lo), hi_count = tiles - min(hi0, tiles);
-    if (b < lo) return b;
-    if (b < lo + hi_count) return hi0 + (b - lo);
-    return b - hi_count;
-}
-
-// A slab without particles still owes its neighbours the epoch of every step.
-__global__ void halo_publish_kernel(StepArgs a) {
-    if (threadIdx.x == 0 && blockIdx.x == 0) halo_publish_empty(a);
-}
-
-// Cursor + wall force, pair sum, kick + drift and the two stores of one particle (shared by all step kernels).
-template <bool M6 = false>
-__device__ __forceinline__ void finish_particle(uint32_t i, uint2 pi, float2 vi, uint32_t cell, float sum_x, float sum_y,
-                                                float scale_x, float scale_y, const StepArgs& a) {
-    float2 f = field_force<M6>(pi, a.ph);
-    f.x = fmaf(scale_x, sum_x, f.x);
-    f.y = fmaf(scale_y, sum_y, f.y);
-    uint2 po;
-    float2 vo;
-    integrate(pi, vi, f, a.ph, po, vo);
-    a.pos_out[i] = po;
-    a.vel[i] = vo;
-    float4 nb = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (a.nbr_out) {
-        nb = nbr_record(po, cell, a.g, a.pf);
-        a.nbr_out[i] = nb;
-    }
-    if (a.push) halo_push(a, i, po, nb);
-}
-
-template <int KN, int FRAC, bool ANISO, bool CG>
-__device__ __forceinline__ void step_particle(uint32_t i, uint2 pi, float2 vi, uint32_t cell,
-                                              const uint32_t* const cs[3], const uint32_t cs_lo[3],
-                                              const uint2* const pp[3], const uint32_t pp_lo[3], const StepArgs& a) {
-    const Grid& g = a.g;
-    uint32_t cx = cell & (g.bx - 1), cy = cell >> g.lx;
-    uint32_t x0 = cx == 0 ? 0 : cx - 1, x1 = cx == g.bx - 1 ? cx : cx + 1;
-    float2 gx = splat(0.f), gy = splat(0.f);
-#pragma unroll
-    for (int d = 0; d < 3; ++d) {
-        int row = (int)cy + d - 1;
-        if (row < 0 || row >= (int)g.by) continue;
-        uint32_t c0 = ((uint32_t)row << g.lx) + x0, c1 = ((uint32_t)row << g.lx) + x1;
-        uint32_t s = cs[d][c0 - cs_lo[d]], e = cs[d][c1 + 1 - cs_lo[d]];
-        const uint2* win = pp[d] + (s - pp_lo[d]);  // window [s, e) of this row
-        if (d == 1) window_accumulate<KN, FRAC, ANISO, true, CG>(win, (int)(e - s), pi, a.ph, gx, gy);  // contains i
-        else window_accumulate<KN, FRAC, ANISO, false, CG>(win, (int)(e - s), pi, a.ph, gx, gy);
-    }
-    finish_particle<(KN > 0)>(i, pi, vi, cell, gx.x + gx.y, gy.x + gy.y, a.ph.pair_scale, a.ph.pair_scale_y, a);
-}
-
-template <int KN, int FRAC, bool ANISO>
-__global__ void __launch_bounds__(kTile, 8) step_kernel(const StepArgs a) {
-    __shared__ __align__(16) uint32_t s_cs[3][kCsCap];
-    __shared__ __align__(16) uint2 s_pos[3][kPosCap];
-    __shared__ __align__(8) uint64_t s_bar;
-
-    const uint32_t b = halo_tile_order(a, blockIdx.x, gridDim.x);
-    const uint32_t i = a.own_lo + b * kTile + threadIdx.x;
-    const TileDesc t = a.tiles[b];
-
-    if (a.push) {  // uniform over the grid
-        if (threadIdx.x == 0) {
-            if (blockIdx.x == 0) halo_publish_empty(a);
-            halo_wait(a, b);
-        }
-        if (!t.fits) __syncthreads();  // the global-memory path reads the ghost rows directly
-    }
-    if (t.fits) {
-        if (threadIdx.x == 0) {
-            mbar_init(&s_bar, 1);
-            uint32_t bytes = 0;
-#pragma unroll
-            for (int d = 0; d < 3; ++d) bytes += t.cs_cnt[d] * 4u + t.p_cnt[d] * 8u;
-            mbar_arrive_expect_tx(&s_bar, bytes);
-#pragma unroll
-            for (int d = 0; d < 3; ++d) {
-                if (t.cs_cnt[d]) bulk_copy_g2s(s_cs[d], a.cell_start + t.cs_lo[d], t.cs_cnt[d] * 4u, &s_bar);
-                if (t.p_cnt[d]) bulk_copy_g2s(s_pos[d], a.pos_in + t.p_lo[d], t.p_cnt[d] * 8u, &s_bar);
-            }
-        }
-        __syncthreads();  // the barrier is initialised before anyone polls it
-    }
-    const bool live = i < a.own_hi;
-    uint2 pi = make_uint2(0, 0);
-    float2 vi = make_float2(0.f, 0.f);
-    uint32_t cell = 0;
-    if (live) {
-        pi = a.pos_in[i];
-        vi = a.vel[i];
-        cell = a.cell_id[i];
-    }
-    if (t.fits) {
-        mbar_wait(&s_bar, 0);
-        if (!live) return;
-        const uint32_t* cs[3] = {s_cs[0], s_cs[1], s_cs[2]};
-        const uint2* pp[3] = {s_pos[0], s_pos[1], s_pos[2]};
-        step_particle<KN, FRAC, ANISO, false>(i, pi, vi, cell, cs, t.cs_lo, pp, t.p_lo, a);
-    } else {
-        if (!live) return;
-        const uint32_t* cs[3] = {a.cell_start, a.cell_start, a.cell_start};
-        const uint2* pp[3] = {a.pos_in, a.pos_in, a.pos_in};
-        const uint32_t zero[3] = {0, 0, 0};
-        step_particle<KN, FRAC, ANISO, true>(i, pi, vi, cell, cs, zero, pp, zero, a);
-    }
-}
-
-// ------------------------------------------------------------------------------------------------
-// DataStructure::CompactArray (kernel_compact.cuh:4-34): every particle interacts with every other one, particles
-// keep their input order, there is no grid. O(N^2): the reference's teaching baseline, offered so that the
-// metadata's data_structure switch (kernel.cuh:143-150) means here what it means there. One thread per particle;
-// the array streams through shared memory 128 positions at a time; same pair arithmetic as step_kernel, with
-// f_dist's unsigned separation (two particles can be more than half the box apart).
-// ------------------------------------------------------------------------------------------------
-template <int KN, int FRAC, bool ANISO>
-__global__ void __launch_bounds__(kTile) allpairs_step_kernel(const StepArgs a) {
-    __shared__ uint2 s_pos[kTile];
-    const uint32_t n = a.own_hi;
-    const uint32_t i = blockIdx.x * kTile + threadIdx.x;
-    const bool live = i < n;
-    const uint2 pi = live ? a.pos_in[i] : make_uint2(0, 0);
-    float2 gx = splat(0.f), gy = splat(0.f);
-    for (uint32_t base = 0; base < n; base += kTile) {
-        __syncthreads();
-        if (base + threadIdx.x < n) s_pos[threadIdx.x] = a.pos_in[base + threadIdx.x];
-        __syncthreads();
-        const int count = (int)min((uint32_t)kTile, n - base);
-        int k = 0;
-        for (; k + 1 < count; k += 2)  // j == i contributes an exact 0 (the clamp), like the reference's `continue`
-            pair2<KN, FRAC, ANISO, false, true, true>(pi, s_pos[k], s_pos[k + 1], a.ph, gx, gy);
-        if (k < count) pair2<KN, FRAC, ANISO, true, true, true>(pi, s_pos[k], pi, a.ph, gx, gy);
-    }
-    if (live) finish_particle(i, pi, a.vel[i], 0u, gx.x + gx.y, gy.x + gy.y, a.ph.pair_scale, a.ph.pair_scale_y, a);
-}
-
-// CompactArray ingest: wire-format records (already free of nulls) -> the structure of arrays, input order kept.
-__global__ void unpack_kernel(const Particle* __restrict__ rec, uint32_t n, uint2* __restrict__ pos,
-                              float2* __restrict__ vel, int32_t* __restrict__ ty, uint32_t* __restrict__ cell_id) {
-    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    const Particle q = rec[i];
-    pos[i] = make_uint2(q.x, q.y);
-    vel[i] = make_float2(q.vx, q.vy);
-    ty[i] = q.ty;
-    cell_id[i] = 0;
-}
-
+#include "device_common.cuh"
+#include "step_int.cuh"
 #include "step_float.cuh"
-
-// ------------------------------------------------------------------------------------------------
-// Binning: stable counting sort by cell (count -> scan -> scatter -> order fix-up + gather).
-//
-//   key_count : key = cell(pos); rank = atomicAdd(count[key], 1)          (arbitrary rank in cell)
-//   scan      : cell_start = exclusive prefix sum of count                 (3 small kernels)
-//   scatter   : perm[cell_start[key] + rank] = candidate index
-//   gather    : slot p holds candidate c = perm[p]; its final place inside its cell is the number of
-//               cell-mates with a smaller candidate index, which makes the result the STABLE sort
-//               whatever order the atomics were served in -- the order the reference's serial
-//               append (kernel.cuh:219-229) and its (row, column, slot) pull (kernel_bucket.cuh:17-33)
-//               both produce.
-// The candidates are, in this order: wire-format records ahead of the live state (an ingested frame,
-// or the particles that migrated in from the lower slab), the live particles this stepper owns, and
-// records behind them (migrants from the upper slab) -- the order those particles have in the global
-// cell-sorted array, so that a slab-decomposed run sorts exactly like a single-slab one.
-// ------------------------------------------------------------------------------------------------
-
-struct Source {
-    const Particle* aos_lo;  // records that sort ahead of the live state (may contain nulls, ty < 0)
-    uint32_t n_lo;
-    const uint2* pos;  // the live state, particles [soa_lo, soa_lo + n_soa)
-    const float2* vel;
-    const int32_t* ty;
-    uint32_t soa_lo, n_soa;
-    const Particle* aos_hi;  // records that sort behind it
-    uint32_t n_hi;
-    uint32_t strict;  // 1: a record outside the owned rows is an error (migrants), 0: it is skipped (ingest)
-};
-
-__device__ __forceinline__ uint32_t source_count(const Source& s) { return s.n_lo + s.n_soa + s.n_hi; }
-
-// Position / velocity / label of candidate c; returns false for a null record (kernel.cuh:222).
-__device__ __forceinline__ bool source_fetch(const Source& s, uint32_t c, uint2& pos, float2& vel, int32_t& ty,
-                                             bool& is_record) {
-    const Particle* rec = nullptr;
-    if (c < s.n_lo) rec = s.aos_lo + c;
-    else if (c >= s.n_lo + s.n_soa) rec = s.aos_hi + (c - s.n_lo - s.n_soa);
-    is_record = rec != nullptr;
-    if (rec) {
-        Particle q = *rec;
-        pos = make_uint2(q.x, q.y);
-        vel = make_float2(q.vx, q.vy);
-        ty = q.ty;
-        return q.ty >= 0;
-    }
-    uint32_t i = s.soa_lo + (c - s.n_lo);
-    pos = s.pos[i];
-    vel = s.vel[i];
-    ty = s.ty[i];
-    return true;
-}
-
-// device-side error bits (PsimStepper::d_flags[0])
-constexpr uint32_t kErrMigrantOutside = 1u;   // a migrant record does not belong to this slab
-constexpr uint32_t kErrMigrantOverflow = 2u;  // more migrants than the exchange boxes hold
-constexpr uint32_t kErrMigrantTooFar = 4u;    // a particle left for a slab that is not adjacent
-
-__global__ void key_count_kernel(Source src, Grid g, uint32_t* __restrict__ cell_count, uint32_t* __restrict__ rank,
-                                 uint32_t* __restrict__ flags) {
-    uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= source_count(src)) return;
-    uint2 pos;
-    float2 vel;
-    int32_t ty;
-    bool is_record;
-    if (!source_fetch(src, c, pos, vel, ty, is_record)) return;
-    uint32_t key = cell_of(pos, g);
-    if (key >= kKeyUp) {  // outside the owned rows: filtered (ingest) or already extracted (live state)
-        if (is_record && src.strict) atomicOr(flags, kErrMigrantOutside);
-        return;
-    }
-    rank[c] = atomicAdd(&cell_count[key], 1u);
-}
-
-// PAD: scan the counts rounded up to even (pad_start of the fp32 step kernel) instead of the counts.
-template <bool PAD>
-__device__ __forceinline__ uint32_t scan_item(uint32_t v) {
-    return PAD ? (v + 1u) & ~1u : v;
-}
-
-template <bool PAD>
-__global__ void __launch_bounds__(kScanThreads) scan_reduce_kernel(const uint32_t* __restrict__ in, uint32_t count,
-                                                                   uint32_t* __restrict__ block_sum) {
-    __shared__ uint32_t warp_sum[kScanThreads / 32];
-    uint32_t base = blockIdx.x * kScanBlock + threadIdx.x * kScanItems;
-    uint32_t v = 0;
-#pragma unroll
-    for (int k = 0; k < kScanItems; ++k)
-        if (base + k < count) v += scan_item<PAD>(in[base + k]);
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xFFFFFFFFu, v, o);
-    if ((threadIdx.x & 31) == 0) warp_sum[threadIdx.x >> 5] = v;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        uint32_t t = 0;
-        for (int w = 0; w < kScanThreads / 32; ++w) t += warp_sum[w];
-        block_sum[blockIdx.x] = t;
-    }
-}
-
-// single block: exclusive scan of block_sum in place, total -> *total_out
-__global__ void __launch_bounds__(1024) scan_top_kernel(uint32_t* __restrict__ block_sum, uint32_t blocks,
-                                                        uint32_t* __restrict__ total_out) {
-    __shared__ uint32_t warp_sum[32];
-    __shared__ uint32_t carry;
-    if (threadIdx.x == 0) carry = 0;
-    __syncthreads();
-    for (uint32_t base = 0; base < blocks; base += 1024) {
-        uint32_t idx = base + threadIdx.x;
-        uint32_t v = idx < blocks ? block_sum[idx] : 0;
-        uint32_t incl = v;
-        for (int o = 1; o < 32; o <<= 1) {
-            uint32_t t = __shfl_up_sync(0xFFFFFFFFu, incl, o);
-            if ((threadIdx.x & 31) >= o) incl += t;
-        }
-        if ((threadIdx.x & 31) == 31) warp_sum[threadIdx.x >> 5] = incl;
-        __syncthreads();
-        if (threadIdx.x < 32) {
-            uint32_t w = warp_sum[threadIdx.x], wi = w;
-            for (int o = 1; o < 32; o <<= 1) {
-                uint32_t t = __shfl_up_sync(0xFFFFFFFFu, wi, o);
-                if (threadIdx.x >= o) wi += t;
-            }
-            warp_sum[threadIdx.x] = wi - w;  // exclusive
-        }
-        __syncthreads();
-        uint32_t excl = carry + warp_sum[threadIdx.x >> 5] + incl - v;
-        if (idx < blocks) block_sum[idx] = excl;
-        __syncthreads();
-        if (threadIdx.x == 1023) carry = excl + v;
-        __syncthreads();
-    }
-    if (threadIdx.x == 0) *total_out = carry;
-}
-
-template <bool PAD>
-__global__ void __launch_bounds__(kScanThreads) scan_apply_kernel(const uint32_t* __restrict__ in, uint32_t count,
-                                                                  const uint32_t* __restrict__ block_offset,
-                                                                  uint32_t* __restrict__ out) {
-    __shared__ uint32_t warp_sum[kScanThreads / 32];
-    uint32_t base = blockIdx.x * kScanBlock + threadIdx.x * kScanItems;
-    uint32_t v[kScanItems];
-    uint32_t t = 0;
-#pragma unroll
-    for (int k = 0; k < kScanItems; ++k) {
-        v[k] = base + k < count ? scan_item<PAD>(in[base + k]) : 0;
-        t += v[k];
-    }
-    uint32_t incl = t;
-    for (int o = 1; o < 32; o <<= 1) {
-        uint32_t u = __shfl_up_sync(0xFFFFFFFFu, incl, o);
-        if ((threadIdx.x & 31) >= o) incl += u;
-    }
-    if ((threadIdx.x & 31) == 31) warp_sum[threadIdx.x >> 5] = incl;
-    __syncthreads();
-    uint32_t woff = 0;
-    for (int w = 0; w < (int)(threadIdx.x >> 5); ++w) woff += warp_sum[w];
-    uint32_t run = block_offset[blockIdx.x] + woff + incl - t;
-#pragma unroll
-    for (int k = 0; k < kScanItems; ++k) {
-        if (base + k < count) out[base + k] = run;
-        run += v[k];
-    }
-}
-
-__global__ void scatter_kernel(Source src, Grid g, const uint32_t* __restrict__ cell_start,
-                               const uint32_t* __restrict__ rank, uint32_t* __restrict__ perm) {
-    uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= source_count(src)) return;
-    uint2 pos;
-    float2 vel;
-    int32_t ty;
-    bool is_record;
-    if (!source_fetch(src, c, pos, vel, ty, is_record)) return;
-    uint32_t key = cell_of(pos, g);
-    if (key >= kKeyUp) return;
-    perm[cell_start[key] + rank[c]] = c;
-}
-
-// Slots [p_lo, p_hi) of the sorted arrays are the owned rows; ghost rows are filled by the exchange.
-__global__ void gather_kernel(Source src, uint32_t p_lo, uint32_t p_hi, Grid g,
-                              const uint32_t* __restrict__ cell_start, const uint32_t* __restrict__ perm,
-                              uint2* __restrict__ pos_out, float2* __restrict__ vel_out,
-                              int32_t* __restrict__ ty_out, uint32_t* __restrict__ cell_id_out,
-                              float4* __restrict__ nbr_out, PhysF pf) {
-    uint32_t p = p_lo + blockIdx.x * blockDim.x + threadIdx.x;
-    if (p >= p_hi) return;
-    uint32_t c = perm[p];
-    uint2 pos;
-    float2 vel;
-    int32_t ty;
-    bool is_record;
-    source_fetch(src, c, pos, vel, ty, is_record);
-    uint32_t key = cell_of(pos, g);
-    uint32_t s = cell_start[key], e = cell_start[key + 1];
-    uint32_t r = 0;
-    for (uint32_t k = s; k < e; ++k) r += perm[k] < c ? 1u : 0u;
-    uint32_t dst = s + r;
-    pos_out[dst] = pos;
-    vel_out[dst] = vel;
-    ty_out[dst] = ty;
-    cell_id_out[dst] = key;
-    if (nbr_out) nbr_out[dst] = nbr_record(pos, key, g, pf);
-}
-
-// Neighbour records of particles [lo, hi) from their positions and membership cells (found in cell_start): ghost
-// rows that arrived as bare positions, or everything after the metadata changed the scale.
-__global__ void nbr_rebuild_kernel(const uint2* __restrict__ pos, const uint32_t* __restrict__ cell_start, Grid g,
-                                   PhysF pf, uint32_t lo, uint32_t hi, float4* __restrict__ nbr) {
-    const uint32_t i = lo + blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= hi) return;
-    nbr[i] = nbr_record(pos[i], (uint32_t)last_le(cell_start, (int)g.cells, i), g, pf);
-}
-
-// The few numbers the host needs after a binning: where the owned rows and their two boundary rows
-// start and end in the sorted arrays. out[0] = own_lo, [1] = end of the first owned row,
-// [2] = start of the last owned row, [3] = own_hi, [4] = total (with ghost rows), [5] = error flags,
-// [6] = tiles of step_kernel_c, [7] = its tiles of the first owned row, [8] = its first tile of the last owned row.
-// The start of the upper ghost row is also published in the slab's HaloHeader for the lower neighbour's pushes.
-constexpr uint32_t kErrHaloTimeout = 8u;  // a step waited 20 s for a neighbour's halo
-__global__ void slab_counts_kernel(const uint32_t* __restrict__ cell_start, Grid g, const uint32_t* __restrict__ flags,
-                                   const uint32_t* __restrict__ couple_tiles, const uint32_t* __restrict__ tile_base,
-                                   HaloHeader* __restrict__ hdr, uint32_t* __restrict__ out) {
-    if (threadIdx.x != 0 || blockIdx.x != 0) return;
-    out[6] = couple_tiles ? *couple_tiles : 0u;  // tiles of step_kernel_c (step_float.cuh)
-    out[7] = tile_base ? tile_base[1] : 0u;
-    out[8] = tile_base ? tile_base[g.own_rows - 1] : 0u;
-    if (hdr) {
-        hdr->own_hi = cell_start[(g.own_row0 + g.own_rows) * g.bx];
-        out[5] = flags[0] | (hdr->error ? kErrHaloTimeout : 0u);
-        out[0] = cell_start[g.own_row0 * g.bx];
-        out[1] = cell_start[(g.own_row0 + 1) * g.bx];
-        out[2] = cell_start[(g.own_row0 + g.own_rows - 1) * g.bx];
-        out[3] = hdr->own_hi;
-        out[4] = cell_start[g.cells];
-        return;
-    }
-    out[0] = cell_start[g.own_row0 * g.bx];
-    out[1] = cell_start[(g.own_row0 + 1) * g.bx];
-    out[2] = cell_start[(g.own_row0 + g.own_rows - 1) * g.bx];
-    out[3] = cell_start[(g.own_row0 + g.own_rows) * g.bx];
-    out[4] = cell_start[g.cells];
-    out[5] = flags[0];
-}
-
-// Cell ids of a ghost row: its particles arrive as bare positions; the ids are needed by nobody (ghosts
-// are never stepped) -- but the row's cell_start entries are, and those come from the scan.
-
-// One descriptor per tile of kTile consecutive OWNED particles: the cell range of the tile, and for each
-// of the three stencil rows the (16-byte aligned) slices of cell_start and of the position array that its
-// CTA stages in shared memory (see step_kernel).
-__global__ void tile_desc_kernel(const uint32_t* __restrict__ cell_start, Grid g, uint32_t own_lo, uint32_t own_hi,
-                                 TileDesc* __restrict__ tiles) {
-    uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
-    uint32_t ntiles = (own_hi - own_lo + kTile - 1) / kTile;
-    if (b >= ntiles) return;
-    uint32_t i0 = own_lo + b * kTile, i1 = min(own_hi, i0 + kTile) - 1;
-    TileDesc t;
-    t.first = (uint32_t)last_le(cell_start, (int)g.cells, i0);
-    t.last = (uint32_t)last_le(cell_start, (int)g.cells, i1);
-    t._pad = 0;
-    bool fits = true;
-    for (int d = 0; d < 3; ++d) {
-        long long shift = (long long)(d - 1) * (long long)g.bx;
-        long long lo = max((long long)t.first - 1 + shift, 0ll);
-        long long hi = min((long long)t.last + 1 + shift, (long long)g.cells - 1);
-        if (hi < lo) {  // the whole row lies outside the grid
-            t.cs_lo[d] = t.cs_cnt[d] = t.p_lo[d] = t.p_cnt[d] = 0;
-            continue;
-        }
-        uint32_t cs_lo = (uint32_t)lo & ~3u;
-        uint32_t cs_cnt = (((uint32_t)hi + 2 - cs_lo) + 3u) & ~3u;  // entries lo .. hi+1
-        uint32_t p_lo = cell_start[lo] & ~1u;
-        uint32_t p_cnt = ((cell_start[hi + 1] - p_lo) + 1u) & ~1u;
-        t.cs_lo[d] = cs_lo;
-        t.cs_cnt[d] = cs_cnt;
-        t.p_lo[d] = p_lo;
-        t.p_cnt[d] = p_cnt;
-        fits = fits && cs_cnt <= (uint32_t)kCsCap && p_cnt <= (uint32_t)kPosCap;
-    }
-    t.fits = fits ? 1u : 0u;
-    tiles[b] = t;
-}
-
-// snapshot: pack the owned particles back into wire-format records (particle.rs:10-18)
-// With stride > 1 only every stride-th particle of the (cell-sorted, hence spatially coherent) state is packed: a
-// decimated snapshot for display, 1/stride of the bytes to copy out and send.
-__global__ void pack_kernel(const uint2* __restrict__ pos, const float2* __restrict__ vel,
-                            const int32_t* __restrict__ ty, uint32_t lo, uint32_t hi, uint32_t stride,
-                            Particle* __restrict__ out) {
-    const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
-    const uint64_t i64 = (uint64_t)lo + (uint64_t)k * stride;
-    if (i64 >= hi) return;
-    const uint32_t i = (uint32_t)i64;
-    uint2 p = pos[i];
-    float2 v = vel[i];
-    Particle q;
-    q.x = p.x;
-    q.y = p.y;
-    q.vx = v.x;
-    q.vy = v.y;
-    q.ty = ty[i];
-    out[k] = q;
-}
-
-// ------------------------------------------------------------------------------------------------
-// Migration between slabs at re-bin time: owned particles whose position left the owned rows are
-// collected (atomics, arbitrary order), then written to a fixed-size box in ascending index order
-// (= the order they have in the global sorted array) for the neighbour to merge.
-// ------------------------------------------------------------------------------------------------
-
-struct MigrantBoxHeader {
-    uint32_t count;
-    uint32_t _pad[3];
-};
-
-__global__ void migrant_extract_kernel(const uint2* __restrict__ pos, uint32_t own_lo, uint32_t own_hi, Grid g,
-                                       uint32_t box_capacity, uint32_t* __restrict__ counters,
-                                       uint32_t* __restrict__ idx_down, uint32_t* __restrict__ idx_up,
-                                       uint32_t* __restrict__ flags) {
-    uint32_t i = own_lo + blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= own_hi) return;
-    uint2 p = pos[i];
-    uint32_t key = cell_of(p, g);
-    if (key < kKeyUp) return;
-    int32_t row = (int32_t)(p.y >> g.sy) - g.row_offset;
-    // anything beyond the adjacent slabs cannot be delivered
-    if (row < (int32_t)g.own_row0 - (int32_t)g.rows_below || row >= (int32_t)(g.own_row0 + g.own_rows + g.rows_above))
-        atomicOr(flags, kErrMigrantTooFar);
-    uint32_t dir = key == kKeyDown ? 0u : 1u;
-    uint32_t slot = atomicAdd(&counters[dir], 1u);
-    if (slot >= box_capacity) {
-        atomicOr(flags, kErrMigrantOverflow);
-        return;
-    }
-    (dir == 0 ? idx_down : idx_up)[slot] = i;
-}
-
-__global__ void migrant_pack_kernel(const uint2* __restrict__ pos, const float2* __restrict__ vel,
-                                    const int32_t* __restrict__ ty, const uint32_t* __restrict__ counter,
-                                    const uint32_t* __restrict__ idx, uint32_t box_capacity,
-                                    unsigned char* __restrict__ box) {
-    uint32_t count = min(*counter, box_capacity);
-    MigrantBoxHeader* header = reinterpret_cast<MigrantBoxHeader*>(box);
-    Particle* rec = reinterpret_cast<Particle*>(box + sizeof(MigrantBoxHeader));
-    uint32_t e = blockIdx.x * blockDim.x + threadIdx.x;
-    if (e == 0) {
-        header->count = count;
-        header->_pad[0] = header->_pad[1] = header->_pad[2] = 0;
-    }
-    if (e >= box_capacity) return;
-    if (e >= count) {  // the rest of the box is null records (ty < 0): the receiver scans the whole box
-        Particle q;
-        q.x = q.y = 0;
-        q.vx = q.vy = 0.f;
-        q.ty = -1;
-        rec[e] = q;
-        return;
-    }
-    uint32_t i = idx[e];
-    uint32_t r = 0;
-    for (uint32_t k = 0; k < count; ++k) r += idx[k] < i ? 1u : 0u;
-    Particle q;
-    uint2 p = pos[i];
-    float2 v = vel[i];
-    q.x = p.x;
-    q.y = p.y;
-    q.vx = v.x;
-    q.vy = v.y;
-    q.ty = ty[i];
-    rec[r] = q;
-}
+#include "binning.cuh"
 
 }  // namespace
 
