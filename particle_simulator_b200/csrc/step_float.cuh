@@ -195,25 +195,90 @@ __global__ void couple_build_kernel(const uint32_t* __restrict__ cell_start, con
     for (uint32_t m = 0; m < n; m += 2, ++k) couple_i0[k] = make_uint2((s + m) | (m + 1 < n ? 0x80000000u : 0u), c);
 }
 
-// How many tiles a row of `m` couples gets: enough for 128 couples per tile AND for at most kTileCols occupied columns
-// per tile (a thin row -- one couple per cell -- next to a thick one would otherwise make tiles so wide that the
-// neighbour rows overflow the staging buffers); the row's couples are then split evenly over its tiles.
+// Cutting a row's couples into tiles (one thread per row, twice: to count the tiles, then to write their spans).
+//
+// The row is looked at in aligned blocks of kTileCols columns. A block is DENSE when it holds at least kSparseCouples
+// couples, or holds anything at all next to such a block (the rim of a droplet belongs to the droplet). A maximal run of
+// dense blocks is cut like this: enough tiles for 128 couples per tile AND for at most kTileCols occupied columns per
+// tile (a thin row -- one couple per cell -- next to a thick one would otherwise make tiles so wide that the neighbour
+// rows overflow the staging buffers), the run's couples split evenly over them. A run of SPARSE blocks (thin gas in an
+// otherwise empty box) is not worth staging -- column-capped tiles would be CTAs with a handful of live threads, and
+// their number would follow the area of the box rather than the particles -- so it gets full tiles as wide as they
+// come; tile_build_kernel finds that those do not fit the staging buffers and they run from global memory.
+// A row that is dense from its first particle to its last (a crystal, a liquid) is one run.
 constexpr int kTileCols = 64;
-__device__ __forceinline__ uint32_t tiles_of_row(const uint32_t* __restrict__ cell_start, const Grid& g, uint32_t row,
-                                                 uint32_t m) {
+constexpr uint32_t kSparseCouples = 32;
+
+template <bool EMIT>
+__device__ __forceinline__ uint32_t cut_run(const uint32_t* __restrict__ cell_start, uint32_t c0, uint32_t b0, uint32_t b1,
+                                            uint32_t k0, uint32_t k1, bool dense, uint32_t first_tile,
+                                            TileC* __restrict__ tiles) {
+    const uint32_t m = k1 - k0;
     if (m == 0) return 0;
-    const uint32_t c0 = row << g.lx, p0 = cell_start[c0], p1 = cell_start[c0 + g.bx];
-    // first occupied column: the last cell whose start is still p0; last occupied: the last cell that starts below p1
-    const uint32_t first = (uint32_t)last_le(cell_start + c0, (int)g.bx, p0);
-    const uint32_t last = (uint32_t)last_le(cell_start + c0, (int)g.bx, p1 - 1);
-    const uint32_t cols = last - first + 1;
-    return max((m + kCouples - 1) / kCouples, (cols + kTileCols - 1) / kTileCols);
+    uint32_t n = (m + kCouples - 1) / kCouples;
+    if (dense) {
+        const uint32_t* cs = cell_start + c0 + b0 * kTileCols;
+        const int ncols = (int)((b1 - b0) * kTileCols);
+        // first occupied column: the last cell whose start is still the run's; last occupied: the last cell that starts
+        // below the run's end
+        const uint32_t first = (uint32_t)last_le(cs, ncols, cs[0]);
+        const uint32_t last = (uint32_t)last_le(cs, ncols, cs[ncols] - 1);
+        n = max(n, (last - first + kTileCols) / kTileCols);
+    }
+    if (EMIT) {
+        const uint32_t per = (m + n - 1) / n;  // <= kCouples
+        for (uint32_t t = 0; t < n; ++t) {
+            const uint32_t k = k0 + t * per;
+            tiles[first_tile + t].k0 = k;
+            tiles[first_tile + t].nk = k < k1 ? min(k1 - k, per) : 0u;  // the even split can leave the last tile empty
+        }
+    }
+    return n;
 }
 
-// Tiles of every owned row (tiles_of_row); single block: exclusive scan into tile_base[0..own_rows], total -> *total_out.
-__global__ void __launch_bounds__(1024) row_tiles_kernel(const uint32_t* __restrict__ cell_start,
-                                                         const uint32_t* __restrict__ pad_start, Grid g,
-                                                         uint32_t* __restrict__ tile_base, uint32_t* __restrict__ total_out) {
+// EMIT = false: tile_base[r] = number of tiles of owned row r (row_tiles_kernel turns the counts into bases in place).
+// EMIT = true: tiles[tile_base[r] ..] get their k0 / nk.
+template <bool EMIT>
+__global__ void row_cut_kernel(const uint32_t* __restrict__ cell_start, const uint32_t* __restrict__ pad_start, Grid g,
+                               uint32_t* __restrict__ tile_base, TileC* __restrict__ tiles) {
+    const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= g.own_rows) return;
+    const uint32_t c0 = (g.own_row0 + r) << g.lx;
+    const uint32_t nb = g.bx / kTileCols;
+    const uint32_t base = EMIT ? tile_base[r] : 0u;
+    uint32_t k_at = pad_start[c0] >> 1;  // first couple of block b
+    uint32_t k_end = pad_start[c0 + kTileCols] >> 1;
+    uint32_t cnt_prev = 0, cnt_cur = k_end - k_at;
+    uint32_t run_k0 = k_at, run_b0 = 0, n = 0;
+    bool run_dense = false;
+    for (uint32_t b = 0; b < nb; ++b) {
+        uint32_t cnt_next = 0;
+        if (b + 1 < nb) {
+            const uint32_t k_next_end = pad_start[c0 + (b + 2) * kTileCols] >> 1;
+            cnt_next = k_next_end - k_end;
+            k_end = k_next_end;
+        }
+        const bool dense = cnt_cur >= kSparseCouples || (cnt_cur > 0 && (cnt_prev >= kSparseCouples || cnt_next >= kSparseCouples));
+        if (b == 0) {
+            run_dense = dense;
+        } else if (dense != run_dense) {
+            n += cut_run<EMIT>(cell_start, c0, run_b0, b, run_k0, k_at, run_dense, base + n, tiles);
+            run_k0 = k_at;
+            run_b0 = b;
+            run_dense = dense;
+        }
+        k_at += cnt_cur;
+        cnt_prev = cnt_cur;
+        cnt_cur = cnt_next;
+    }
+    n += cut_run<EMIT>(cell_start, c0, run_b0, nb, run_k0, k_at, run_dense, base + n, tiles);
+    if (!EMIT) tile_base[r] = n;
+}
+
+// Tiles of every owned row (row_cut_kernel<false> left the counts in tile_base); single block: exclusive scan in place
+// into tile_base[0..own_rows], total -> *total_out.
+__global__ void __launch_bounds__(1024) row_tiles_kernel(Grid g, uint32_t* __restrict__ tile_base,
+                                                         uint32_t* __restrict__ total_out) {
     __shared__ uint32_t warp_sum[32];
     __shared__ uint32_t carry;
     if (threadIdx.x == 0) carry = 0;
@@ -221,11 +286,7 @@ __global__ void __launch_bounds__(1024) row_tiles_kernel(const uint32_t* __restr
     for (uint32_t base = 0; base < g.own_rows; base += 1024) {
         const uint32_t r = base + threadIdx.x;
         uint32_t v = 0;
-        if (r < g.own_rows) {
-            const uint32_t row = g.own_row0 + r;
-            const uint32_t m = (pad_start[(row + 1) << g.lx] - pad_start[row << g.lx]) >> 1;
-            v = tiles_of_row(cell_start, g, row, m);
-        }
+        if (r < g.own_rows) v = tile_base[r];
         uint32_t incl = v;
         for (int o = 1; o < 32; o <<= 1) {
             uint32_t u = __shfl_up_sync(0xFFFFFFFFu, incl, o);
@@ -254,7 +315,7 @@ __global__ void __launch_bounds__(1024) row_tiles_kernel(const uint32_t* __restr
     }
 }
 
-// One TileC per tile index b in [0, tile_base[own_rows]).
+// One TileC per tile index b in [0, tile_base[own_rows]); row_cut_kernel<true> has written its k0 / nk.
 __global__ void tile_build_kernel(const uint32_t* __restrict__ cell_start, const uint32_t* __restrict__ pad_start,
                                   const uint32_t* __restrict__ tile_base, const uint2* __restrict__ couple_i0,
                                   Grid g, TileC* __restrict__ tiles) {
@@ -263,12 +324,9 @@ __global__ void tile_build_kernel(const uint32_t* __restrict__ cell_start, const
     // the last row whose base is <= b (rows without tiles share their successor's base and are skipped over)
     const uint32_t r = (uint32_t)last_le(tile_base, (int)g.own_rows, b);
     const uint32_t row = g.own_row0 + r;
-    const uint32_t row_k0 = pad_start[row << g.lx] >> 1, row_k1 = pad_start[(row + 1) << g.lx] >> 1;
-    const uint32_t row_tiles = tile_base[r + 1] - tile_base[r];
-    const uint32_t per_tile = (row_k1 - row_k0 + row_tiles - 1) / row_tiles;  // <= kCouples, even split
     TileC t;
-    t.k0 = row_k0 + (b - tile_base[r]) * per_tile;
-    t.nk = t.k0 < row_k1 ? min(row_k1 - t.k0, per_tile) : 0u;  // the even split can leave a row's last tile empty
+    t.k0 = tiles[b].k0;
+    t.nk = tiles[b].nk;
     t.row = row;
     if (t.nk == 0) {  // nothing to step: no staging either
         t.fits = 0;

@@ -640,8 +640,10 @@ int enqueue_scan(PsimStepper* s) {
         scan_top_kernel<<<1, 1024, 0, s->stream>>>(s->block_sum, blocks, s->pad_start + cells);
         scan_apply_kernel<true><<<blocks, kScanThreads, 0, s->stream>>>(s->cell_count, cells, s->block_sum, s->pad_start);
         couple_build_kernel<<<div_up(cells, 256), 256, 0, s->stream>>>(s->cell_start, s->pad_start, cells, s->couple_i0);
-        row_tiles_kernel<<<1, 1024, 0, s->stream>>>(s->cell_start, s->pad_start, s->grid, s->tile_base, s->d_couple_tiles);
-        s->launches += 5;
+        row_cut_kernel<false><<<div_up(s->grid.own_rows, 64), 64, 0, s->stream>>>(s->cell_start, s->pad_start, s->grid,
+                                                                                s->tile_base, s->tiles_c);
+        row_tiles_kernel<<<1, 1024, 0, s->stream>>>(s->grid, s->tile_base, s->d_couple_tiles);
+        s->launches += 6;
     }
     CK(cudaGetLastError());
     return PSIM_OK;
@@ -783,6 +785,9 @@ int bin_phase_tiles(PsimStepper* s) {
     tile_desc_kernel<<<div_up(tiles, 128), 128, 0, s->stream>>>(s->cell_start, s->grid, s->own_lo, s->own_hi, s->tiles);
     s->launches += 1;
     if (s->float_grid && s->n_tiles_c) {
+        row_cut_kernel<true><<<div_up(s->grid.own_rows, 64), 64, 0, s->stream>>>(s->cell_start, s->pad_start, s->grid,
+                                                                               s->tile_base, s->tiles_c);
+        s->launches += 1;
         tile_build_kernel<<<div_up(s->n_tiles_c, 128), 128, 0, s->stream>>>(s->cell_start, s->pad_start, s->tile_base,
                                                                           s->couple_i0, s->grid, s->tiles_c);
         s->launches += 1;
@@ -1383,9 +1388,9 @@ int psim_create(const PsimConfig* config, PsimStepper** out) {
     if (st->float_grid) {
         // couples: every particle, plus one half-empty couple per cell at most
         const size_t couples = (cap_total + std::min<size_t>(cap_total, g.cells)) / 2 + 1;
-        // per row: ceil(couples / 128) or ceil(occupied columns / kTileCols), whichever is larger
-        st->tiles_c_cap = (uint32_t)((cap + std::min<size_t>(cap, (size_t)g.own_rows * g.bx)) / 2 / kCouples + g.own_rows + 1 +
-                                     (size_t)g.own_rows * (g.bx / kTileCols + 1));
+        // per run of blocks of a row (row_cut_kernel): at most ceil(couples / 128) + its blocks; at most one run per block
+        st->tiles_c_cap = (uint32_t)((cap + std::min<size_t>(cap, (size_t)g.own_rows * g.bx)) / 2 / kCouples + 1 +
+                                     (size_t)g.own_rows * (2 * (g.bx / kTileCols) + 1));
         CKC(cudaMalloc(&st->pad_start, sizeof(uint32_t) * ((size_t)g.cells + 1 + kPadCells)));
         CKC(cudaMemset(st->pad_start, 0, sizeof(uint32_t) * ((size_t)g.cells + 1 + kPadCells)));
         CKC(cudaMalloc(&st->couple_i0, sizeof(uint2) * couples));
