@@ -62,6 +62,10 @@ struct Phys {
     int wall_m6;         // m == 6: wall term by multiplication
     int cursor_on;       // the cursor can reach a particle of the box at all
     float m;
+    // A particle further than this from a wall (fixed-point units) skips that wall's term: beyond
+    // d = sigma 10^(8/(m+1)) the term is below 1e-8 C eps m / sigma, i.e. < 1e-7 of the largest attraction between two
+    // particles and less than one fp32 rounding of any force sum that matters (0xFFFFFFFF: never skip; make_phys).
+    uint32_t wall_skip_x, wall_skip_y;
 };
 
 // One tile of kTile consecutive particles: what its CTA stages in shared memory. Written at re-bin
@@ -275,10 +279,17 @@ __device__ __forceinline__ float2 field_force(uint2 p, const Phys& ph) {
             f.y = dy > 0 ? -c : c;
         }
     }
-    if (p.x < 0xFFFFFFFFu / 2) f.x += wall_term<M6>(__uint2float_rn(p.x) * ph.kx, ph);
-    else f.x -= wall_term<M6>(__uint2float_rn(0xFFFFFFFFu - p.x) * ph.kx, ph);
-    if (p.y < 0xFFFFFFFFu / 2) f.y += wall_term<M6>(__uint2float_rn(p.y) * ph.ky, ph);
-    else f.y -= wall_term<M6>(__uint2float_rn(0xFFFFFFFFu - p.y) * ph.ky, ph);
+    // nearest wall per axis (particle.cuh:125-144: side chosen by p.x < UINT32_MAX / 2), one term per axis
+    const bool left = p.x < 0xFFFFFFFFu / 2, low = p.y < 0xFFFFFFFFu / 2;
+    const uint32_t dxw = left ? p.x : 0xFFFFFFFFu - p.x, dyw = low ? p.y : 0xFFFFFFFFu - p.y;
+    if (dxw <= ph.wall_skip_x) {
+        const float w = wall_term<M6>(__uint2float_rn(dxw) * ph.kx, ph);
+        f.x += left ? w : -w;
+    }
+    if (dyw <= ph.wall_skip_y) {
+        const float w = wall_term<M6>(__uint2float_rn(dyw) * ph.ky, ph);
+        f.y += low ? w : -w;
+    }
     return f;
 }
 

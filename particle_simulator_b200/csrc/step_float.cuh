@@ -35,12 +35,19 @@ constexpr int kColCap = 128;   // cell columns a tile's stencil rows may span (i
 constexpr int kCsRow = 136;    // cell_start entries staged per row: kColCap + 1, + 3 alignment slack, multiple of 4
 constexpr int kRowCap = 448;   // neighbour records staged per stencil row (a crystal at r0 has rows of 6 per cell)
 constexpr int kCouples = 128;  // couples (= threads) per tile
+#ifndef PSIM_MIN_CTAS
+#define PSIM_MIN_CTAS 9  // CTAs per SM the register allocation aims at (56 registers per thread)
+#endif
+#ifndef PSIM_PAIR_UNROLL
+#define PSIM_PAIR_UNROLL 1
+#endif
+constexpr int kPairUnroll = PSIM_PAIR_UNROLL;  // neighbours per trip of the pair loops
 
 // One tile: couples [k0, k0 + nk) of local cell row `row`.
 struct __align__(16) TileC {
     uint32_t k0, nk;
     uint32_t row;
-    uint32_t fits;        // 0: a stencil row exceeds the staging buffers -> global-memory path
+    uint32_t fits;        // bytes staged in shared memory; 0: a stencil row exceeds the staging buffers -> global-memory path
     uint32_t cs_lo[3];    // first cell_start entry staged per row (multiple of 4)
     uint32_t cs_cnt[3];   // entries staged per row (multiple of 4; 0: row outside the grid)
     uint32_t p_lo[3];     // first particle staged per row (even)
@@ -65,7 +72,12 @@ __device__ __forceinline__ void pairc(float xj, float yj, float2 nx, float2 ny, 
         r2.x = fmaxf(r2.x, 1e-3f);
         r2.y = fmaxf(r2.y, 1e-3f);
     }
+#ifdef PSIM_SHARED_RCP  // one MUFU.RCP for both lanes: 1 / (a b), times b and a (A/B switch)
+    const float rr = fast_rcp(r2.x * r2.y);
+    float2 q = make_float2(r2.y * rr, r2.x * rr);
+#else
     float2 q = make_float2(fast_rcp(r2.x), fast_rcp(r2.y));
+#endif
     float2 q2 = __fmul2_rn(q, q);
     float2 q4 = __fmul2_rn(q2, q2);
     float2 pn;
@@ -90,7 +102,7 @@ __device__ __forceinline__ void pairc(float xj, float yj, float2 nx, float2 ny, 
 }
 
 template <int KN, int FRAC>
-__global__ void __launch_bounds__(kCouples, 9) step_kernel_c(const StepArgs a, const StepArgsC ac) {
+__global__ void __launch_bounds__(kCouples, PSIM_MIN_CTAS) step_kernel_c(const StepArgs a, const StepArgsC ac) {
     __shared__ __align__(16) float4 s_nb[3][kRowCap];     // neighbour records of the three stencil rows
     __shared__ __align__(16) uint32_t s_cs[3][kCsRow];    // their cell_start slices
     __shared__ __align__(8) uint64_t s_bar;
@@ -121,17 +133,26 @@ __global__ void __launch_bounds__(kCouples, 9) step_kernel_c(const StepArgs a, c
     }
 
     // TMA: the cell_start slices and the neighbour records of the three stencil rows (through L2: a ghost row is
-    // written by the neighbour slab while this kernel runs)
-    if (threadIdx.x == 0) {
-        mbar_init(&s_bar, 1);
-        uint32_t bytes = 0;
-#pragma unroll
-        for (int d = 0; d < 3; ++d) bytes += t.cs_cnt[d] * 4u + t.p_cnt[d] * 16u;
-        mbar_arrive_expect_tx(&s_bar, bytes);
-#pragma unroll
-        for (int d = 0; d < 3; ++d) {
-            if (t.cs_cnt[d]) bulk_copy_g2s(s_cs[d], a.cell_start + t.cs_lo[d], t.cs_cnt[d] * 4u, &s_bar);
-            if (t.p_cnt[d]) bulk_copy_g2s(s_nb[d], a.nbr_in + t.p_lo[d], t.p_cnt[d] * 16u, &s_bar);
+    // written by the neighbour slab while this kernel runs). Six lanes of warp 0 issue one 1-D bulk copy each.
+    if (threadIdx.x < 32) {
+        if (threadIdx.x == 0) {
+            mbar_init(&s_bar, 1);
+            mbar_arrive_expect_tx(&s_bar, t.fits);
+        }
+        __syncwarp();
+        if (threadIdx.x < 6) {
+            // ghost rows were written by the neighbour GPU through the generic proxy; the bulk copies read through the
+            // async proxy: order them after thread 0's acquire in halo_wait
+            if (a.push) asm volatile("fence.proxy.async.global;" ::: "memory");
+            const uint32_t d = threadIdx.x >> 1;
+            const uint32_t* tw = reinterpret_cast<const uint32_t*>(ac.tiles + tile);  // cs_lo @4, cs_cnt @7, p_lo @10, p_cnt @13
+            if (threadIdx.x & 1) {
+                const uint32_t lo = tw[10 + d], cnt = tw[13 + d];
+                if (cnt) bulk_copy_g2s(s_nb[d], a.nbr_in + lo, cnt * 16u, &s_bar);
+            } else {
+                const uint32_t lo = tw[4 + d], cnt = tw[7 + d];
+                if (cnt) bulk_copy_g2s(s_cs[d], a.cell_start + lo, cnt * 4u, &s_bar);
+            }
         }
     }
 
@@ -170,16 +191,18 @@ __global__ void __launch_bounds__(kCouples, 9) step_kernel_c(const StepArgs a, c
         // a neighbour in the row below / above sits one row distance further down / up than its own-row offset says
         const float2 ny = __fadd2_rn(ny0, splat((float)(d - 1) * pf.row_shift));
         // (x_even, y) or (x_odd, y): the 8 bytes at offset 0 or 8 of a record
-        const float4* nb = s_nb[d] + ws;
-        const float4* const nb_end = s_nb[d] + we;
-        for (; nb < nb_end; ++nb) {
-            const float2 j = reinterpret_cast<const float2*>(nb)[par];
+        const float2* pj = reinterpret_cast<const float2*>(s_nb[d] + ws) + par;
+        const float2* const pj_end = reinterpret_cast<const float2*>(s_nb[d] + we);
+#pragma unroll kPairUnroll
+        for (; pj < pj_end; pj += 2) {
+            const float2 j = *pj;
             if (d == 1) pairc<KN, FRAC, true>(j.x, j.y, nx, ny, pf, gx, gy);
             else pairc<KN, FRAC, false>(j.x, j.y, nx, ny, pf, gx, gy);
         }
     }
-    finish_particle<true>(i0, p0, v0, cell, gx.x, gy.x, pf.pair_scale, pf.pair_scale, a);  // KN > 0 implies m == 6
-    if (has1) finish_particle<true>(i1, p1, v1, cell, gx.y, gy.y, pf.pair_scale, pf.pair_scale, a);
+    const RecOrigin org = rec_origin(cell, g, pf);  // both particles are members of the same cell
+    finish_particle<true>(i0, p0, v0, cell, gx.x, gy.x, pf.pair_scale, pf.pair_scale, a, &org);  // KN > 0 implies m == 6
+    if (has1) finish_particle<true>(i1, p1, v1, cell, gx.y, gy.y, pf.pair_scale, pf.pair_scale, a, &org);
 }
 
 // ---- re-bin side of the couples ------------------------------------------------------------------------
@@ -339,6 +362,7 @@ __global__ void tile_build_kernel(const uint32_t* __restrict__ cell_start, const
     const uint32_t col_lo = c_first == 0 ? 0 : c_first - 1;
     const uint32_t col_hi = c_last == g.bx - 1 ? c_last : c_last + 1;
     bool fits = col_hi - col_lo + 1 <= (uint32_t)kColCap;
+    uint32_t bytes = 0;
     for (int d = 0; d < 3; ++d) {
         const long long rd = (long long)row + d - 1;
         if (rd < 0 || rd >= (long long)g.by) {
@@ -351,7 +375,8 @@ __global__ void tile_build_kernel(const uint32_t* __restrict__ cell_start, const
         t.p_lo[d] = cell_start[lo] & ~1u;
         t.p_cnt[d] = ((cell_start[hi + 1] - t.p_lo[d]) + 1u) & ~1u;
         fits = fits && t.cs_cnt[d] <= (uint32_t)kCsRow && t.p_cnt[d] <= (uint32_t)kRowCap;
+        bytes += t.cs_cnt[d] * 4u + t.p_cnt[d] * 16u;
     }
-    t.fits = fits ? 1u : 0u;
+    t.fits = fits ? bytes : 0u;
     tiles[b] = t;
 }

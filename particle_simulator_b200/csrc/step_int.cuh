@@ -101,16 +101,33 @@ struct StepArgs {
     PhysF pf;
 };
 
-// The neighbour record of a particle at `p` whose membership cell is `cell` (local numbering).
-__device__ __forceinline__ float4 nbr_record(uint2 p, uint32_t cell, const Grid& g, const PhysF& pf) {
+// Where the offsets of a neighbour record are measured from: the centre of the membership cell's even zone span (x),
+// the centre of its row (y), and the signed distance to the odd zone's origin. The same for all particles of a cell.
+struct RecOrigin {
+    uint32_t xo0, yc;
+    float odd_shift;
+};
+
+__device__ __forceinline__ RecOrigin rec_origin(uint32_t cell, const Grid& g, const PhysF& pf) {
     const uint32_t cx = cell & (g.bx - 1);
     const long long row = (long long)(cell >> g.lx) + g.row_offset;              // global cell row
-    const uint32_t yc = (uint32_t)((2ll * row + 1) << (g.sy - 1));               // centre of that row
     const uint32_t zq = cx >> pf.zl;
-    const uint32_t xo0 = (((zq & ~1u) << pf.zl) << pf.sxbits) + pf.half_span;    // centre of the even zone's span
-    const float xe = __int2float_rn((int)(p.x - xo0)) * pf.sx;
-    const float y = __int2float_rn((int)(p.y - yc)) * pf.sy;
-    return make_float4(xe, y, xe + ((zq & 1u) ? -pf.zone_shift : pf.zone_shift), y);
+    RecOrigin o;
+    o.yc = (uint32_t)((2ll * row + 1) << (g.sy - 1));                            // centre of that row
+    o.xo0 = (((zq & ~1u) << pf.zl) << pf.sxbits) + pf.half_span;                 // centre of the even zone's span
+    o.odd_shift = (zq & 1u) ? -pf.zone_shift : pf.zone_shift;
+    return o;
+}
+
+__device__ __forceinline__ float4 nbr_record(uint2 p, const RecOrigin& o, const PhysF& pf) {
+    const float xe = __int2float_rn((int)(p.x - o.xo0)) * pf.sx;
+    const float y = __int2float_rn((int)(p.y - o.yc)) * pf.sy;
+    return make_float4(xe, y, xe + o.odd_shift, y);
+}
+
+// The neighbour record of a particle at `p` whose membership cell is `cell` (local numbering).
+__device__ __forceinline__ float4 nbr_record(uint2 p, uint32_t cell, const Grid& g, const PhysF& pf) {
+    return nbr_record(p, rec_origin(cell, g, pf), pf);
 }
 
 // Before a tile that reads a ghost row stages anything: wait for the neighbour's previous step (one thread).
@@ -178,10 +195,12 @@ __global__ void halo_publish_kernel(StepArgs a) {
     if (threadIdx.x == 0 && blockIdx.x == 0) halo_publish_empty(a);
 }
 
-// Cursor + wall force, pair sum, kick + drift and the two stores of one particle (shared by all step kernels).
+// Cursor + wall force, pair sum, kick + drift and the stores of one particle (shared by all step kernels).
+// `origin`: where the particle's neighbour record is measured from (null: derived from `cell` when records are kept).
 template <bool M6 = false>
 __device__ __forceinline__ void finish_particle(uint32_t i, uint2 pi, float2 vi, uint32_t cell, float sum_x, float sum_y,
-                                                float scale_x, float scale_y, const StepArgs& a) {
+                                                float scale_x, float scale_y, const StepArgs& a,
+                                                const RecOrigin* origin = nullptr) {
     float2 f = field_force<M6>(pi, a.ph);
     f.x = fmaf(scale_x, sum_x, f.x);
     f.y = fmaf(scale_y, sum_y, f.y);
@@ -191,7 +210,10 @@ __device__ __forceinline__ void finish_particle(uint32_t i, uint2 pi, float2 vi,
     a.pos_out[i] = po;
     a.vel[i] = vo;
     float4 nb = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (a.nbr_out) {
+    if (origin) {
+        nb = nbr_record(po, *origin, a.pf);
+        a.nbr_out[i] = nb;
+    } else if (a.nbr_out) {
         nb = nbr_record(po, cell, a.g, a.pf);
         a.nbr_out[i] = nb;
     }

@@ -329,6 +329,16 @@ Phys make_phys(const FrameMetadata& m, int* kernel_kn, int* kernel_frac, bool* a
     ph.pair_scale_y = ph.pair_scale;
     ph.wall_scale = C * p.epsilon * p.m;
     ph.wall_m6 = p.m == 6.f;
+    {   // where a wall's term stops mattering (Phys::wall_skip_x): d = sigma 10^(8 / (m + 1)), in fixed-point units
+        const double d_skip = (double)p.sigma * std::pow(10.0, 8.0 / ((double)p.m + 1.0));
+        auto units = [&](double box) {
+            const double u = d_skip / box * 4294967296.0;
+            return p.m > 0.f && u < 2147483647.0 ? (uint32_t)u : 0xFFFFFFFFu;
+        };
+        ph.wall_skip_x = units(m.box_width);
+        ph.wall_skip_y = units(m.box_height);
+        if (getenv("PSIM_NO_WALL_SKIP")) ph.wall_skip_x = ph.wall_skip_y = 0xFFFFFFFFu;
+    }
     ph.sigma = p.sigma;
     ph.inv_mass = 1.f / (float)6.63352599e-26;  // particle.cuh:51
     ph.dt = m.step_dt;
@@ -886,11 +896,8 @@ int enqueue_step(PsimStepper* s) {
     a.pf = s->physf;
     a.nbr_in = a.nbr_out = nullptr;
     if (s->float_path && !s->compact_mode) {
-        if (s->nbr_stale) {  // new scale (metadata) or records not kept so far: rebuild them from the positions
-            int rc = enqueue_nbr_rebuild(s, 0, s->n_total);
-            if (rc) return rc;
-            s->nbr_stale = false;
-        }
+        if (s->nbr_stale)  // team_step rebuilds stale records before it enqueues a step
+            return fail(s, PSIM_ESTATE, "internal: a step was enqueued on stale neighbour records");
         a.nbr_in = s->nbr[s->cur_pos];
         a.nbr_out = s->nbr[s->cur_pos ^ 1];
     }
@@ -953,10 +960,44 @@ int enqueue_step(PsimStepper* s) {
     return PSIM_OK;
 }
 
+// New metadata (another scale of the neighbour records, or records that were not kept so far): rebuild the records of
+// the positions the next step reads. A slab rebuilds its OWN rows only. Its ghost rows may still be receiving the
+// positions and old-scale records its neighbours' last step pushes (that step is not waited for here), so they are
+// delivered again by an explicit exchange of the boundary rows -- ordered after the neighbours' last step by the
+// transport -- and converted on arrival; the next step then has nothing to wait for, exactly as after a binning.
+int team_refresh_stale_records(const Team& t) {
+    bool any = false;
+    for (int r = 0; r < t.count; ++r) {
+        const PsimStepper* s = t.ranks[r];
+        any = any || (s->float_path && !s->compact_mode && s->nbr_stale);
+    }
+    if (!any) return PSIM_OK;
+    int rc;
+    const bool redeliver = t.ranks[0]->nranks > 1 && t.ranks[0]->push && t.ranks[0]->ghosts_by_push;
+    for (int r = 0; r < t.count; ++r) {
+        PsimStepper* s = t.ranks[r];
+        if (redeliver) rc = enqueue_nbr_rebuild(s, s->own_lo, s->own_hi);
+        else rc = enqueue_nbr_rebuild(s, 0, s->n_total);  // ghost rows are in place (a binning or an exchange put them there)
+        if (rc) return rc;
+    }
+    if (redeliver) {
+        std::vector<XferOp> ops(t.count);
+        for (int r = 0; r < t.count; ++r) ops[r] = ghost_positions_op(t.ranks[r]);
+        if ((rc = team_exchange(t, ops))) return rc;
+        for (int r = 0; r < t.count; ++r) {
+            if ((rc = refresh_ghost_records(t.ranks[r]))) return rc;
+            t.ranks[r]->ghosts_by_push = false;
+        }
+    }
+    for (int r = 0; r < t.count; ++r) t.ranks[r]->nbr_stale = false;
+    return PSIM_OK;
+}
+
 // One leapfrog step of every slab, then the halo exchange: each slab's new boundary-row positions
 // become its neighbours' ghost rows for the next step.
 int team_step(const Team& t) {
     int rc;
+    if ((rc = team_refresh_stale_records(t))) return rc;
     for (int r = 0; r < t.count; ++r) {
         if ((rc = enqueue_step(t.ranks[r]))) return rc;
         t.ranks[r]->fresh_scene = false;

@@ -67,7 +67,7 @@ def lib() -> ctypes.CDLL:
     """Load libpsim_b200.so; raises if it has not been built (the product has no other path)."""
     global _lib
     if _lib is None:
-        path = _build.LIB_PSIM
+        path = os.environ.get("PSIM_LIB") or _build.LIB_PSIM  # PSIM_LIB: another build of the same library (A/B runs)
         if not os.path.exists(path):
             raise PsimError(f"{path} is missing: run `python -m particle_simulator_b200._build` "
                             "(there is no CPU fallback for the stepper)")

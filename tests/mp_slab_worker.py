@@ -42,7 +42,19 @@ def main() -> int:
         single.upload(wl.frame)
     ok = True
     counts_seen = set()
+    meta_change = os.environ.get("PSIM_TEST_META_CHANGE") == "1"
     for frame in range(frames + 1):
+        if frame >= 2 and meta_change:
+            # a header-only metadata update between frames: another sigma (frame 2), then another box (frame 3) --
+            # the neighbour records change scale while the ghost rows are being pushed (team_refresh_stale_records)
+            m = wl.frame.metadata.copy()
+            m["particles"][0]["sigma"] = np.float32(3.609e-10 * (1.0 + 0.01 * frame))
+            if frame >= 3:
+                m["box_width"] = np.float32(float(m["box_width"]) * 1.005)
+                m["box_height"] = np.float32(float(m["box_height"]) * 1.005)
+            st.set_metadata(m)
+            if single:
+                single.set_metadata(m)
         if frame:
             st.run_frame_async()
             st.sync()

@@ -30,7 +30,12 @@ def test_nccl_slabs_of_unequal_heights():
     run_workers(2, "push", bounds="0,448,1024", port=29650)
 
 
-def run_workers(world, halo, bounds=None, port=None):
+def test_nccl_slabs_metadata_change_between_frames():
+    """New sigma / box between frames while the halo is pushed: own rows rebuilt locally, ghost rows re-delivered."""
+    run_workers(2, "push", port=29660, meta_change=True)
+
+
+def run_workers(world, halo, bounds=None, port=None, meta_change=False):
     if _gpus() < world:
         pytest.skip(f"needs {world} GPUs, this box has {_gpus()}")
     env = dict(os.environ, PSIM_EXPECT_HALO=halo)
@@ -38,6 +43,8 @@ def run_workers(world, halo, bounds=None, port=None):
         env["PSIM_TEST_BOUNDS"] = bounds
     if halo == "nccl":
         env["PSIM_HALO"] = "nccl"
+    if meta_change:
+        env["PSIM_TEST_META_CHANGE"] = "1"
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}",
            "--master-addr", "127.0.0.1", "--master-port", str(port or 29600 + world + (10 if halo == "nccl" else 0)),
            os.path.join(REPO, "tests", "mp_slab_worker.py"), "3"]

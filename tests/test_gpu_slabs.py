@@ -101,6 +101,36 @@ def test_balanced_boundaries_and_rebalancing_a_running_group():
                 assert [s.slab_info()["first_row"] for s in gr.slabs] == new[:-1]
 
 
+def test_metadata_change_between_frames_on_pushed_halo_fine_grid():
+    """A header-only metadata update (Kernel::write_metadata, kernel.cuh:96-101) that changes the scale of the
+    neighbour records (sigma, then the box) while the ghost rows are being filled by the neighbours' pushes: the
+    slabs rebuild their own rows and re-deliver the ghost rows (team_refresh_stale_records, stepper.cu). Bit-identical
+    to the single slab, which rebuilds everything locally."""
+    from particle_simulator_b200 import workloads
+    from particle_simulator_b200.stepper import SlabGroup, Stepper
+
+    w = workloads.clustered_mixed((10, 10), clusters=4, side=120, gas=8000, seed=7)
+    w.frame.metadata["steps_per_frame"] = 20
+    n = w.particles
+    metas = [w.frame.metadata.copy() for _ in range(3)]
+    metas[1]["particles"][0]["sigma"] = np.float32(3.7e-10)
+    metas[2]["box_width"] = np.float32(float(metas[2]["box_width"]) * 1.01)
+    metas[2]["box_height"] = np.float32(float(metas[2]["box_height"]) * 1.01)
+    with Stepper(w.grid_log2, n) as st, SlabGroup(w.grid_log2, 4, n, ingest_capacity=n) as gr:
+        st.upload(w.frame)
+        gr.upload(w.frame)
+        assert gr.slabs[1].tile_stats()["float_path"] == 1 and gr.slabs[1].halo_mode == 2
+        for m in metas:
+            st.set_metadata(m)
+            gr.set_metadata(m)
+            for _ in range(2):
+                st.run_frame_async()
+                gr.run_frame_async()
+                st.sync()
+                gr.sync()
+                assert st.download().particles.tobytes() == gr.download().particles.tobytes()
+
+
 def test_ingest_and_fine_grained_calls_match(golden):
     from particle_simulator_b200.stepper import SlabGroup, Stepper
 
