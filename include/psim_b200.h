@@ -96,7 +96,10 @@ int psim_upload_frame(PsimStepper* s, const FrameHeader* frame);
 /* Same, for particle records that already live in device memory (AoS, 20 B each). */
 int psim_upload_device(PsimStepper* s, const FrameMetadata* meta, const void* d_particles, uint32_t count);
 
-/* = Kernel::write_metadata (kernel.cuh:96-101): takes effect for the next frame that is enqueued. */
+/* = Kernel::write_metadata (kernel.cuh:96-101): takes effect for the next frame that is enqueued.
+ * One deviation: the reference picks its layout from every frame's metadata (kernel.cuh:143-150); here the layout is
+ * the one the scene was uploaded in, so an update whose data_structure differs from it returns PSIM_EINVAL and changes
+ * nothing (upload the scene again to switch between MatrixBuckets and CompactArray). */
 int psim_set_metadata(PsimStepper* s, const FrameMetadata* meta);
 int psim_get_metadata(const PsimStepper* s, FrameMetadata* out);
 
@@ -159,6 +162,7 @@ uint32_t psim_particle_count(const PsimStepper* s);          /* live particles o
 uint64_t psim_steps_executed(const PsimStepper* s);          /* leapfrog steps enqueued so far    */
 uint64_t psim_rebins_executed(const PsimStepper* s);         /* re-binning passes enqueued so far */
 uint64_t psim_kernel_launches(const PsimStepper* s);         /* kernels of this library launched  */
+uint64_t psim_migrants_sent(const PsimStepper* s);           /* particles handed to neighbour slabs by re-bins */
 uint32_t psim_cell_count(const PsimStepper* s);              /* BX * BY                           */
 /* cell_start[0..cells] of the current binning (cells+1 entries, exclusive prefix sum of the per-cell
  * particle counts; synchronises). */
@@ -188,6 +192,10 @@ int psim_tile_stats(PsimStepper* s, PsimTileStats* out);
  * bounds[k-1 .. k+2] clamped to the array (psim_slab_bounds_of). Re-balancing a running decomposition = download,
  * psim_balance_rows on the snapshot, re-create the steppers, upload. */
 int psim_balance_rows(const FrameHeader* scene, uint32_t grid_y_log2, uint32_t slab_count, uint32_t* bounds);
+/* The same cut from a histogram: row_counts[r] = live particles in global cell row r (1 << grid_y_log2 entries). With one
+ * process per slab every rank histograms its own particles, the histograms are summed over the ranks (one all-reduce)
+ * and every rank cuts the same boundaries (particle_simulator_b200/slabs.py: rebalance_across_ranks). */
+int psim_balance_rows_hist(const uint64_t* row_counts, uint32_t grid_y_log2, uint32_t slab_count, uint32_t* bounds);
 void psim_slab_bounds_of(const uint32_t* bounds, uint32_t slab_rank, uint32_t slab_count, uint32_t out[4]);
 
 /* Where this stepper's slab sits and what it currently holds. */

@@ -41,6 +41,32 @@ int psim_scene_gas(FrameHeader* frame, uint32_t capacity, uint32_t count, double
 /* r0 = sigma * (n/m)^(1/(n-m)), the zero-force distance (particle.rs:44-49), in double like the reference. */
 double psim_force0_r(MiePotentialParams p);
 
+/*
+ * Scene presets: `Preset` and `Presets` of particle_io/src/presets.rs:84-154, the in-memory scene library the editor
+ * keeps ("User Presets", particle_editor/src/editor.rs:961-1072). A preset holds what a scene is made of -- a name, the
+ * box size, the two species' Mie parameters and the particle list -- and nothing of how it is stepped.
+ * The list is an opaque handle; indices are positions in it. Functions return 0 on success and -1 on a null or
+ * out-of-range argument (where the reference would panic on the index), except where stated.
+ */
+typedef struct PsimPresets PsimPresets;
+
+PsimPresets* psim_presets_new(void);                          /* Presets::new, presets.rs:127-129 */
+void psim_presets_destroy(PsimPresets* presets);
+size_t psim_presets_len(const PsimPresets* presets);          /* get_presets_len, presets.rs:131-133 */
+/* add_preset(Preset::from_frame(name, frame)), presets.rs:107-119,139-141: box, species and all particle_count records
+ * of `frame` (null records included, like particles().to_vec()). Returns the new preset's index, or -1. */
+long psim_presets_add_from_frame(PsimPresets* presets, const char* name, const FrameHeader* frame);
+/* change_preset(Preset::from_frame(name, frame), index), presets.rs:147-153: an index past the end is IGNORED (returns 0). */
+int psim_presets_change_from_frame(PsimPresets* presets, size_t index, const char* name, const FrameHeader* frame);
+/* add_preset(get_preset(index).clone()) under another name (the editor's "duplicate", editor.rs:998-1000); returns the new index */
+long psim_presets_duplicate(PsimPresets* presets, size_t index, const char* new_name);
+int psim_presets_delete(PsimPresets* presets, size_t index);  /* delete_preset, presets.rs:143-145 */
+const char* psim_preset_name(const PsimPresets* presets, size_t index);      /* owned by the list; NULL if out of range */
+uint32_t psim_preset_particle_count(const PsimPresets* presets, size_t index);
+/* Preset::to_frame, presets.rs:92-105: a NEW frame -- frame_header_init() defaults -- with the preset's box, species and
+ * particles. `dst` is a caller buffer of packet_size(capacity) bytes; -1 if the preset holds more than `capacity`. */
+int psim_preset_to_frame(const PsimPresets* presets, size_t index, FrameHeader* dst, uint32_t capacity);
+
 #ifdef __cplusplus
 } /* extern "C" */
 #endif

@@ -62,107 +62,131 @@ constexpr uint32_t kErrMigrantTooFar = 4u;    // a particle left for a slab that
 __global__ void key_count_kernel(Source src, Grid g, uint32_t* __restrict__ cell_count, uint32_t* __restrict__ rank,
                                  uint32_t* __restrict__ flags) {
     uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= source_count(src)) return;
-    uint2 pos;
-    float2 vel;
-    int32_t ty;
-    bool is_record;
-    if (!source_fetch(src, c, pos, vel, ty, is_record)) return;
-    uint32_t key = cell_of(pos, g);
-    if (key >= kKeyUp) {  // outside the owned rows: filtered (ingest) or already extracted (live state)
-        if (is_record && src.strict) atomicOr(flags, kErrMigrantOutside);
-        return;
+    uint32_t key = kKeyUp;  // nothing to count: past the end, a null record, or outside the owned rows
+    if (c < source_count(src)) {
+        uint2 pos;
+        float2 vel;
+        int32_t ty;
+        bool is_record;
+        if (source_fetch(src, c, pos, vel, ty, is_record)) {
+            key = cell_of(pos, g);
+            // outside the owned rows: filtered (ingest) or already extracted (live state)
+            if (key >= kKeyUp && is_record && src.strict) atomicOr(flags, kErrMigrantOutside);
+        }
     }
-    rank[c] = atomicAdd(&cell_count[key], 1u);
+    // The candidates are nearly sorted by cell (the live state was sorted by the last binning, scenes are generated
+    // row by row), so the lanes of a warp share a few keys: one atomic per distinct key and warp instead of one per
+    // particle. Inside the group ranks follow the lane order; the gather makes the final order stable anyway.
+    const uint32_t peers = __match_any_sync(0xFFFFFFFFu, key);
+    if (key >= kKeyUp) return;
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint32_t leader = __ffs(peers) - 1u;
+    uint32_t base = 0;
+    if (lane == leader) base = atomicAdd(&cell_count[key], __popc(peers));
+    base = __shfl_sync(peers, base, leader);
+    rank[c] = base + __popc(peers & ((1u << lane) - 1u));
 }
 
-// PAD: scan the counts rounded up to even (pad_start of the fp32 step kernel) instead of the counts.
-template <bool PAD>
-__device__ __forceinline__ uint32_t scan_item(uint32_t v) {
-    return PAD ? (v + 1u) & ~1u : v;
+// The scans produce cell_start (exclusive prefix sum of the counts) and, on fine grids, pad_start (the same over the
+// counts rounded up to even: couples of step_kernel_c) in one pass over cell_count: .x sums the counts, .y the padded ones.
+__device__ __forceinline__ uint2 scan_item(uint32_t v) { return make_uint2(v, (v + 1u) & ~1u); }
+__device__ __forceinline__ uint2 add2(uint2 a, uint2 b) { return make_uint2(a.x + b.x, a.y + b.y); }
+__device__ __forceinline__ uint2 shfl_up2(uint2 v, int o) {
+    return make_uint2(__shfl_up_sync(0xFFFFFFFFu, v.x, o), __shfl_up_sync(0xFFFFFFFFu, v.y, o));
 }
 
-template <bool PAD>
 __global__ void __launch_bounds__(kScanThreads) scan_reduce_kernel(const uint32_t* __restrict__ in, uint32_t count,
-                                                                   uint32_t* __restrict__ block_sum) {
-    __shared__ uint32_t warp_sum[kScanThreads / 32];
+                                                                   uint2* __restrict__ block_sum) {
+    __shared__ uint2 warp_sum[kScanThreads / 32];
     uint32_t base = blockIdx.x * kScanBlock + threadIdx.x * kScanItems;
-    uint32_t v = 0;
+    uint2 v = make_uint2(0, 0);
 #pragma unroll
     for (int k = 0; k < kScanItems; ++k)
-        if (base + k < count) v += scan_item<PAD>(in[base + k]);
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xFFFFFFFFu, v, o);
+        if (base + k < count) v = add2(v, scan_item(in[base + k]));
+    for (int o = 16; o > 0; o >>= 1) {
+        v.x += __shfl_down_sync(0xFFFFFFFFu, v.x, o);
+        v.y += __shfl_down_sync(0xFFFFFFFFu, v.y, o);
+    }
     if ((threadIdx.x & 31) == 0) warp_sum[threadIdx.x >> 5] = v;
     __syncthreads();
     if (threadIdx.x == 0) {
-        uint32_t t = 0;
-        for (int w = 0; w < kScanThreads / 32; ++w) t += warp_sum[w];
+        uint2 t = make_uint2(0, 0);
+        for (int w = 0; w < kScanThreads / 32; ++w) t = add2(t, warp_sum[w]);
         block_sum[blockIdx.x] = t;
     }
 }
 
-// single block: exclusive scan of block_sum in place, total -> *total_out
-__global__ void __launch_bounds__(1024) scan_top_kernel(uint32_t* __restrict__ block_sum, uint32_t blocks,
-                                                        uint32_t* __restrict__ total_out) {
-    __shared__ uint32_t warp_sum[32];
-    __shared__ uint32_t carry;
-    if (threadIdx.x == 0) carry = 0;
+// single block: exclusive scan of block_sum in place, totals -> *total_out (.x) and *pad_total_out (.y, if not null)
+__global__ void __launch_bounds__(1024) scan_top_kernel(uint2* __restrict__ block_sum, uint32_t blocks,
+                                                        uint32_t* __restrict__ total_out, uint32_t* __restrict__ pad_total_out) {
+    __shared__ uint2 warp_sum[32];
+    __shared__ uint2 carry;
+    if (threadIdx.x == 0) carry = make_uint2(0, 0);
     __syncthreads();
     for (uint32_t base = 0; base < blocks; base += 1024) {
         uint32_t idx = base + threadIdx.x;
-        uint32_t v = idx < blocks ? block_sum[idx] : 0;
-        uint32_t incl = v;
+        uint2 v = idx < blocks ? block_sum[idx] : make_uint2(0, 0);
+        uint2 incl = v;
         for (int o = 1; o < 32; o <<= 1) {
-            uint32_t t = __shfl_up_sync(0xFFFFFFFFu, incl, o);
-            if ((threadIdx.x & 31) >= o) incl += t;
+            uint2 t = shfl_up2(incl, o);
+            if ((threadIdx.x & 31) >= o) incl = add2(incl, t);
         }
         if ((threadIdx.x & 31) == 31) warp_sum[threadIdx.x >> 5] = incl;
         __syncthreads();
         if (threadIdx.x < 32) {
-            uint32_t w = warp_sum[threadIdx.x], wi = w;
+            uint2 w = warp_sum[threadIdx.x], wi = w;
             for (int o = 1; o < 32; o <<= 1) {
-                uint32_t t = __shfl_up_sync(0xFFFFFFFFu, wi, o);
-                if (threadIdx.x >= o) wi += t;
+                uint2 t = shfl_up2(wi, o);
+                if (threadIdx.x >= o) wi = add2(wi, t);
             }
-            warp_sum[threadIdx.x] = wi - w;  // exclusive
+            warp_sum[threadIdx.x] = make_uint2(wi.x - w.x, wi.y - w.y);  // exclusive
         }
         __syncthreads();
-        uint32_t excl = carry + warp_sum[threadIdx.x >> 5] + incl - v;
+        uint2 ws = warp_sum[threadIdx.x >> 5];
+        uint2 excl = make_uint2(carry.x + ws.x + incl.x - v.x, carry.y + ws.y + incl.y - v.y);
         if (idx < blocks) block_sum[idx] = excl;
         __syncthreads();
-        if (threadIdx.x == 1023) carry = excl + v;
+        if (threadIdx.x == 1023) carry = add2(excl, v);
         __syncthreads();
     }
-    if (threadIdx.x == 0) *total_out = carry;
+    if (threadIdx.x == 0) {
+        *total_out = carry.x;
+        if (pad_total_out) *pad_total_out = carry.y;
+    }
 }
 
+// PAD: also write pad_start.
 template <bool PAD>
 __global__ void __launch_bounds__(kScanThreads) scan_apply_kernel(const uint32_t* __restrict__ in, uint32_t count,
-                                                                  const uint32_t* __restrict__ block_offset,
-                                                                  uint32_t* __restrict__ out) {
-    __shared__ uint32_t warp_sum[kScanThreads / 32];
+                                                                  const uint2* __restrict__ block_offset,
+                                                                  uint32_t* __restrict__ out, uint32_t* __restrict__ pad_out) {
+    __shared__ uint2 warp_sum[kScanThreads / 32];
     uint32_t base = blockIdx.x * kScanBlock + threadIdx.x * kScanItems;
     uint32_t v[kScanItems];
-    uint32_t t = 0;
+    uint2 t = make_uint2(0, 0);
 #pragma unroll
     for (int k = 0; k < kScanItems; ++k) {
-        v[k] = base + k < count ? scan_item<PAD>(in[base + k]) : 0;
-        t += v[k];
+        v[k] = base + k < count ? in[base + k] : 0;
+        t = add2(t, scan_item(v[k]));
     }
-    uint32_t incl = t;
+    uint2 incl = t;
     for (int o = 1; o < 32; o <<= 1) {
-        uint32_t u = __shfl_up_sync(0xFFFFFFFFu, incl, o);
-        if ((threadIdx.x & 31) >= o) incl += u;
+        uint2 u = shfl_up2(incl, o);
+        if ((threadIdx.x & 31) >= o) incl = add2(incl, u);
     }
     if ((threadIdx.x & 31) == 31) warp_sum[threadIdx.x >> 5] = incl;
     __syncthreads();
-    uint32_t woff = 0;
-    for (int w = 0; w < (int)(threadIdx.x >> 5); ++w) woff += warp_sum[w];
-    uint32_t run = block_offset[blockIdx.x] + woff + incl - t;
+    uint2 woff = make_uint2(0, 0);
+    for (int w = 0; w < (int)(threadIdx.x >> 5); ++w) woff = add2(woff, warp_sum[w]);
+    const uint2 off = block_offset[blockIdx.x];
+    uint2 run = make_uint2(off.x + woff.x + incl.x - t.x, off.y + woff.y + incl.y - t.y);
 #pragma unroll
     for (int k = 0; k < kScanItems; ++k) {
-        if (base + k < count) out[base + k] = run;
-        run += v[k];
+        if (base + k < count) {
+            out[base + k] = run.x;
+            if (PAD) pad_out[base + k] = run.y;
+        }
+        run = add2(run, scan_item(v[k]));
     }
 }
 
@@ -218,14 +242,19 @@ __global__ void nbr_rebuild_kernel(const uint2* __restrict__ pos, const uint32_t
 // The few numbers the host needs after a binning: where the owned rows and their two boundary rows
 // start and end in the sorted arrays. out[0] = own_lo, [1] = end of the first owned row,
 // [2] = start of the last owned row, [3] = own_hi, [4] = total (with ghost rows), [5] = error flags,
-// [6] = tiles of step_kernel_c, [7] = its tiles of the first owned row, [8] = its first tile of the last owned row.
+// [6] = tiles of step_kernel_c, [7] = its tiles of the first owned row, [8] = its first tile of the last owned row,
+// [9] = the tile table overflowed, [10], [11] = migrants of this re-bin to the lower / upper slab.
 // The start of the upper ghost row is also published in the slab's HaloHeader for the lower neighbour's pushes.
 constexpr uint32_t kErrHaloTimeout = 8u;  // a step waited 20 s for a neighbour's halo
 __global__ void slab_counts_kernel(const uint32_t* __restrict__ cell_start, Grid g, const uint32_t* __restrict__ flags,
                                    const uint32_t* __restrict__ couple_tiles, const uint32_t* __restrict__ tile_base,
-                                   HaloHeader* __restrict__ hdr, uint32_t* __restrict__ out) {
+                                   HaloHeader* __restrict__ hdr, const uint32_t* __restrict__ mig_counters,
+                                   uint32_t* __restrict__ out) {
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
-    out[6] = couple_tiles ? *couple_tiles : 0u;  // tiles of step_kernel_c (step_float.cuh)
+    out[10] = mig_counters ? mig_counters[0] : 0u;  // particles this re-bin found below / above the owned rows
+    out[11] = mig_counters ? mig_counters[1] : 0u;
+    out[6] = couple_tiles ? couple_tiles[0] : 0u;  // tiles of step_kernel_c (step_float.cuh)
+    out[9] = couple_tiles ? couple_tiles[1] : 0u;  // ... did not fit the tile table
     out[7] = tile_base ? tile_base[1] : 0u;
     out[8] = tile_base ? tile_base[g.own_rows - 1] : 0u;
     if (hdr) {

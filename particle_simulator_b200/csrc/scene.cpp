@@ -8,6 +8,8 @@
 
 #include <cmath>
 #include <cstdint>
+#include <cstring>
+#include <string>
 #include <vector>
 
 namespace {
@@ -190,6 +192,94 @@ int psim_scene_gas(FrameHeader* frame, uint32_t capacity, uint32_t count, double
         ++placed;
     }
     frame->particle_count += count;
+    return 0;
+}
+
+}  // extern "C"
+
+// ---- presets (particle_io/src/presets.rs:84-154) -----------------------------------------------------------------
+
+namespace {
+struct Preset {  // presets.rs:84-90
+    std::string name;
+    float box_w = 0.f, box_h = 0.f;
+    MiePotentialParams particles[2]{};
+    std::vector<Particle> particles_list;
+};
+
+Preset preset_from_frame(const char* name, const FrameHeader* frame) {  // presets.rs:107-119
+    Preset p;
+    p.name = name ? name : "";
+    p.box_w = frame->metadata.box_width;  // box_size() widens to f64 and from_frame narrows it back: the same f32
+    p.box_h = frame->metadata.box_height;
+    p.particles[0] = frame->metadata.particles[0];
+    p.particles[1] = frame->metadata.particles[1];
+    p.particles_list.assign(frame->particles, frame->particles + frame->particle_count);
+    return p;
+}
+}  // namespace
+
+struct PsimPresets {  // presets.rs:122-124
+    std::vector<Preset> presets;
+};
+
+extern "C" {
+
+PsimPresets* psim_presets_new(void) { return new PsimPresets; }
+
+void psim_presets_destroy(PsimPresets* presets) { delete presets; }
+
+size_t psim_presets_len(const PsimPresets* presets) { return presets ? presets->presets.size() : 0; }
+
+long psim_presets_add_from_frame(PsimPresets* presets, const char* name, const FrameHeader* frame) {
+    if (!presets || !frame) return -1;
+    presets->presets.push_back(preset_from_frame(name, frame));
+    return (long)presets->presets.size() - 1;
+}
+
+int psim_presets_change_from_frame(PsimPresets* presets, size_t index, const char* name, const FrameHeader* frame) {
+    if (!presets || !frame) return -1;
+    if (index >= presets->presets.size()) return 0;  // "why not": presets.rs:148-151 ignores it
+    presets->presets[index] = preset_from_frame(name, frame);
+    return 0;
+}
+
+long psim_presets_duplicate(PsimPresets* presets, size_t index, const char* new_name) {
+    if (!presets || index >= presets->presets.size()) return -1;
+    Preset copy = presets->presets[index];
+    if (new_name) copy.name = new_name;
+    presets->presets.push_back(std::move(copy));
+    return (long)presets->presets.size() - 1;
+}
+
+int psim_presets_delete(PsimPresets* presets, size_t index) {
+    if (!presets || index >= presets->presets.size()) return -1;
+    presets->presets.erase(presets->presets.begin() + (long)index);
+    return 0;
+}
+
+const char* psim_preset_name(const PsimPresets* presets, size_t index) {
+    if (!presets || index >= presets->presets.size()) return nullptr;
+    return presets->presets[index].name.c_str();
+}
+
+uint32_t psim_preset_particle_count(const PsimPresets* presets, size_t index) {
+    if (!presets || index >= presets->presets.size()) return 0;
+    return (uint32_t)presets->presets[index].particles_list.size();
+}
+
+int psim_preset_to_frame(const PsimPresets* presets, size_t index, FrameHeader* dst, uint32_t capacity) {
+    if (!presets || !dst || index >= presets->presets.size()) return -1;
+    const Preset& p = presets->presets[index];
+    if (p.particles_list.size() > capacity) return -1;
+    *dst = frame_header_init();  // Frame::new(): default metadata, no particles
+    dst->metadata.box_width = p.box_w;
+    dst->metadata.box_height = p.box_h;
+    dst->metadata.particles[0] = p.particles[0];
+    dst->metadata.particles[1] = p.particles[1];
+    if (!p.particles_list.empty())
+        std::memcpy(dst->particles, p.particles_list.data(), sizeof(Particle) * p.particles_list.size());
+    dst->particle_count = (uint32_t)p.particles_list.size();
     return 0;
 }
 

@@ -165,7 +165,8 @@ struct Simulator {
             return ok;
         }
         if (in.ptr) {  // interactive mode: only the metadata changes, from the frame after the running one on
-            psim_set_metadata(stepper, &in.ptr->metadata);
+            if (psim_set_metadata(stepper, &in.ptr->metadata) != PSIM_OK)  // e.g. a data_structure switch without a scene
+                std::fprintf(stderr, "psim_simulator: metadata update ignored: %s\n", psim_last_error(stepper));
             frame_destroy(&in);
         }
         // frame k's snapshot (age 1: frame k+1's is enqueued already) is copied out and sent while frame k+1 runs

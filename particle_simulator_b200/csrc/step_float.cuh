@@ -58,6 +58,10 @@ static_assert(sizeof(TileC) == 64, "TileC is read as four 16-byte words");
 struct StepArgsC {
     const uint2* __restrict__ couple_i0;  // per couple: (index of its first particle | (has a second one) << 31, its cell)
     const TileC* __restrict__ tiles;
+    // How many tiles the last binning made, in device memory: the host sizes the launch from the count it last saw
+    // plus a margin (it does not wait for a re-bin to learn the new one), CTAs beyond the count leave at once, and if
+    // the count ever outgrows the launch the first CTAs of the grid step the surplus tiles as well.
+    const uint32_t* __restrict__ n_tiles;
 };
 
 // One staged neighbour (its x offset of the thread's zone parity, its y) against the thread's two particles.
@@ -101,23 +105,26 @@ __device__ __forceinline__ void pairc(float xj, float yj, float2 nx, float2 ny, 
     gy = __ffma2_rn(g, y, gy);
 }
 
+struct SmemC {
+    float4 nb[3][kRowCap];     // neighbour records of the three stencil rows
+    uint32_t cs[3][kCsRow];    // their cell_start slices
+    uint64_t bar;
+};
+
+// One tile: stage its stencil, step its couples.
 template <int KN, int FRAC>
-__global__ void __launch_bounds__(kCouples, PSIM_MIN_CTAS) step_kernel_c(const StepArgs a, const StepArgsC ac) {
-    __shared__ __align__(16) float4 s_nb[3][kRowCap];     // neighbour records of the three stencil rows
-    __shared__ __align__(16) uint32_t s_cs[3][kCsRow];    // their cell_start slices
-    __shared__ __align__(8) uint64_t s_bar;
+__device__ __forceinline__ void step_tile_c(const StepArgs& a, const StepArgsC& ac, uint32_t tile, SmemC& sm) {
+    float4 (&s_nb)[3][kRowCap] = sm.nb;
+    uint32_t (&s_cs)[3][kCsRow] = sm.cs;
+    uint64_t& s_bar = sm.bar;
 
     const Grid& g = a.g;
     const PhysF& pf = a.pf;
-    const uint32_t tile = halo_tile_order(a, blockIdx.x, gridDim.x);
     const TileC t = ac.tiles[tile];
     const bool live = threadIdx.x < t.nk;
 
     if (a.push) {  // uniform over the grid
-        if (threadIdx.x == 0) {
-            if (blockIdx.x == 0) halo_publish_empty(a);
-            halo_wait(a, tile);  // tiles next to a ghost row: the neighbour's last step has landed
-        }
+        if (threadIdx.x == 0) halo_wait(a, tile);  // tiles next to a ghost row: the neighbour's last step has landed
         if (!t.fits) __syncthreads();  // the global-memory path reads the ghost rows directly
     }
     if (!t.fits) {  // very sparse or very crowded spot: same physics straight from global memory, one particle at a time
@@ -205,6 +212,33 @@ __global__ void __launch_bounds__(kCouples, PSIM_MIN_CTAS) step_kernel_c(const S
     if (has1) finish_particle<true>(i1, p1, v1, cell, gx.y, gy.y, pf.pair_scale, pf.pair_scale, a, &org);
 }
 
+// The grid is the tile count the host last saw plus a margin (exactly the count when it has just read it: slabs). The
+// binning writes EMPTY descriptors (nk = 0) behind the last tile up to the size of the launch, so a surplus CTA leaves as
+// soon as it has read its descriptor and nobody waits for the count.
+template <int KN, int FRAC>
+__global__ void __launch_bounds__(kCouples, PSIM_MIN_CTAS) step_kernel_c(const StepArgs a, const StepArgsC ac) {
+    __shared__ __align__(16) SmemC sm;
+    if (a.push && blockIdx.x == 0 && threadIdx.x == 0) halo_publish_empty(a);
+    step_tile_c<KN, FRAC>(a, ac, halo_tile_order(a, blockIdx.x, gridDim.x), sm);
+}
+
+// Surplus TILES: the count grew past the launch, which the host's margin makes rare. A single slab follows every step
+// launch with this one (a few CTAs that read the count from device memory and, almost always, leave): tiles
+// [first, count) in turn. Kept out of step_kernel_c so that the kernel proper is compiled for exactly one tile.
+constexpr uint32_t kSurplusCtas = 128;
+
+template <int KN, int FRAC>
+__global__ void __launch_bounds__(kCouples) step_kernel_c_surplus(const StepArgs a, const StepArgsC ac, uint32_t first) {
+    __shared__ __align__(16) SmemC sm;
+    const uint32_t count = *ac.n_tiles;
+    for (uint32_t tile = first + blockIdx.x; tile < count; tile += gridDim.x) {
+        step_tile_c<KN, FRAC>(a, ac, tile, sm);
+        __syncthreads();  // everybody has left the staging buffers and the barrier before the next tile re-arms them
+        if (threadIdx.x == 0) asm volatile("mbarrier.inval.shared::cta.b64 [%0];" ::"r"(smem_u32(&sm.bar)) : "memory");
+        __syncthreads();
+    }
+}
+
 // ---- re-bin side of the couples ------------------------------------------------------------------------
 
 // couple_i0[k] for the couples of every cell (the cell is the one of this binning, i.e. the membership cell of the
@@ -222,35 +256,50 @@ __global__ void couple_build_kernel(const uint32_t* __restrict__ cell_start, con
 //
 // The row is looked at in aligned blocks of kTileCols columns. A block is DENSE when it holds at least kSparseCouples
 // couples, or holds anything at all next to such a block (the rim of a droplet belongs to the droplet). A maximal run of
-// dense blocks is cut like this: enough tiles for 128 couples per tile AND for at most kTileCols occupied columns per
-// tile (a thin row -- one couple per cell -- next to a thick one would otherwise make tiles so wide that the neighbour
-// rows overflow the staging buffers), the run's couples split evenly over them. A run of SPARSE blocks (thin gas in an
-// otherwise empty box) is not worth staging -- column-capped tiles would be CTAs with a handful of live threads, and
-// their number would follow the area of the box rather than the particles -- so it gets full tiles as wide as they
-// come; tile_build_kernel finds that those do not fit the staging buffers and they run from global memory.
+// dense blocks is cut like this: enough tiles for 128 couples per tile, for at most kTileColsMax occupied columns per
+// tile, AND for each of the three stencil rows over the run's columns to fit the staging buffer (a thin row -- one couple
+// per cell -- next to a thick one would otherwise make tiles whose neighbour rows overflow it); the run's couples are
+// split evenly over them. A gas at 2.4 per cell fills its 128 threads this way (89 columns per tile), a crystal is cut by
+// the couples (58 columns). A run of SPARSE blocks (thin gas in an otherwise empty box) is not worth staging --
+// column-capped tiles would be CTAs with a handful of live threads, and their number would follow the area of the box
+// rather than the particles -- so it gets full tiles as wide as they come; tile_build_kernel finds that those do not fit
+// the staging buffers and they run from global memory.
 // A row that is dense from its first particle to its last (a crystal, a liquid) is one run.
-constexpr int kTileCols = 64;
+constexpr int kTileCols = 64;             // block width of the dense / sparse classification
+constexpr int kTileColsMax = kColCap - 2; // occupied columns a staged tile may span (its stencil rows: +- 1 column)
+constexpr uint32_t kRowFill = 384;        // staged particles per stencil row a cut aims at (kRowCap with slack for uneven rows)
 constexpr uint32_t kSparseCouples = 32;
 
 template <bool EMIT>
-__device__ __forceinline__ uint32_t cut_run(const uint32_t* __restrict__ cell_start, uint32_t c0, uint32_t b0, uint32_t b1,
-                                            uint32_t k0, uint32_t k1, bool dense, uint32_t first_tile,
-                                            TileC* __restrict__ tiles) {
+__device__ __forceinline__ uint32_t cut_run(const uint32_t* __restrict__ cell_start, const Grid& g, uint32_t row, uint32_t b0,
+                                            uint32_t b1, uint32_t k0, uint32_t k1, bool dense, uint32_t first_tile,
+                                            TileC* __restrict__ tiles, uint32_t tiles_cap) {
     const uint32_t m = k1 - k0;
     if (m == 0) return 0;
     uint32_t n = (m + kCouples - 1) / kCouples;
     if (dense) {
+        const uint32_t c0 = row << g.lx;
         const uint32_t* cs = cell_start + c0 + b0 * kTileCols;
         const int ncols = (int)((b1 - b0) * kTileCols);
         // first occupied column: the last cell whose start is still the run's; last occupied: the last cell that starts
         // below the run's end
-        const uint32_t first = (uint32_t)last_le(cs, ncols, cs[0]);
-        const uint32_t last = (uint32_t)last_le(cs, ncols, cs[ncols] - 1);
-        n = max(n, (last - first + kTileCols) / kTileCols);
+        const uint32_t first = b0 * kTileCols + (uint32_t)last_le(cs, ncols, cs[0]);
+        const uint32_t last = b0 * kTileCols + (uint32_t)last_le(cs, ncols, cs[ncols] - 1);
+        n = max(n, (last - first + kTileColsMax) / kTileColsMax);
+        // the three stencil rows over the run's columns +- 1: enough tiles for each to fit the staging buffer when the run's
+        // couples are split evenly (a thin row next to a thick one must not make tiles whose neighbour rows overflow)
+        const uint32_t lo = first == 0 ? 0 : first - 1, hi = min(last + 1, g.bx - 1);
+#pragma unroll
+        for (int d = -1; d <= 1; ++d) {
+            const int rd = (int)row + d;
+            if (rd < 0 || rd >= (int)g.by) continue;
+            const uint32_t* rs = cell_start + ((uint32_t)rd << g.lx);
+            n = max(n, (rs[hi + 1] - rs[lo] + kRowFill - 1) / kRowFill);
+        }
     }
     if (EMIT) {
         const uint32_t per = (m + n - 1) / n;  // <= kCouples
-        for (uint32_t t = 0; t < n; ++t) {
+        for (uint32_t t = 0; t < n && first_tile + t < tiles_cap; ++t) {
             const uint32_t k = k0 + t * per;
             tiles[first_tile + t].k0 = k;
             tiles[first_tile + t].nk = k < k1 ? min(k1 - k, per) : 0u;  // the even split can leave the last tile empty
@@ -263,7 +312,7 @@ __device__ __forceinline__ uint32_t cut_run(const uint32_t* __restrict__ cell_st
 // EMIT = true: tiles[tile_base[r] ..] get their k0 / nk.
 template <bool EMIT>
 __global__ void row_cut_kernel(const uint32_t* __restrict__ cell_start, const uint32_t* __restrict__ pad_start, Grid g,
-                               uint32_t* __restrict__ tile_base, TileC* __restrict__ tiles) {
+                               uint32_t* __restrict__ tile_base, TileC* __restrict__ tiles, uint32_t tiles_cap) {
     const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= g.own_rows) return;
     const uint32_t c0 = (g.own_row0 + r) << g.lx;
@@ -285,7 +334,7 @@ __global__ void row_cut_kernel(const uint32_t* __restrict__ cell_start, const ui
         if (b == 0) {
             run_dense = dense;
         } else if (dense != run_dense) {
-            n += cut_run<EMIT>(cell_start, c0, run_b0, b, run_k0, k_at, run_dense, base + n, tiles);
+            n += cut_run<EMIT>(cell_start, g, g.own_row0 + r, run_b0, b, run_k0, k_at, run_dense, base + n, tiles, tiles_cap);
             run_k0 = k_at;
             run_b0 = b;
             run_dense = dense;
@@ -294,13 +343,13 @@ __global__ void row_cut_kernel(const uint32_t* __restrict__ cell_start, const ui
         cnt_prev = cnt_cur;
         cnt_cur = cnt_next;
     }
-    n += cut_run<EMIT>(cell_start, c0, run_b0, nb, run_k0, k_at, run_dense, base + n, tiles);
+    n += cut_run<EMIT>(cell_start, g, g.own_row0 + r, run_b0, nb, run_k0, k_at, run_dense, base + n, tiles, tiles_cap);
     if (!EMIT) tile_base[r] = n;
 }
 
 // Tiles of every owned row (row_cut_kernel<false> left the counts in tile_base); single block: exclusive scan in place
-// into tile_base[0..own_rows], total -> *total_out.
-__global__ void __launch_bounds__(1024) row_tiles_kernel(Grid g, uint32_t* __restrict__ tile_base,
+// into tile_base[0..own_rows]; total (at most the room in the tile table) -> total_out[0], total_out[1] |= it was more.
+__global__ void __launch_bounds__(1024) row_tiles_kernel(Grid g, uint32_t* __restrict__ tile_base, uint32_t tiles_cap,
                                                          uint32_t* __restrict__ total_out) {
     __shared__ uint32_t warp_sum[32];
     __shared__ uint32_t carry;
@@ -334,16 +383,26 @@ __global__ void __launch_bounds__(1024) row_tiles_kernel(Grid g, uint32_t* __res
     }
     if (threadIdx.x == 0) {
         tile_base[g.own_rows] = carry;
-        *total_out = carry;
+        total_out[0] = min(carry, tiles_cap);
+        if (carry > tiles_cap) total_out[1] = 1u;
     }
 }
 
-// One TileC per tile index b in [0, tile_base[own_rows]); row_cut_kernel<true> has written its k0 / nk.
+// One TileC per tile index b in [0, n_tiles[0]); row_cut_kernel<true> has written its k0 / nk.
 __global__ void tile_build_kernel(const uint32_t* __restrict__ cell_start, const uint32_t* __restrict__ pad_start,
-                                  const uint32_t* __restrict__ tile_base, const uint2* __restrict__ couple_i0,
-                                  Grid g, TileC* __restrict__ tiles) {
+                                  const uint32_t* __restrict__ tile_base, const uint32_t* __restrict__ n_tiles,
+                                  uint32_t clear_upto, const uint2* __restrict__ couple_i0, Grid g,
+                                  TileC* __restrict__ tiles) {
     const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
-    if (b >= tile_base[g.own_rows]) return;
+    if (b >= n_tiles[0]) {  // behind the last tile, as far as a step launches CTAs: empty descriptors
+        if (b < clear_upto) {
+            TileC t;
+            t.k0 = t.nk = t.row = t.fits = 0;
+            for (int d = 0; d < 3; ++d) t.cs_lo[d] = t.cs_cnt[d] = t.p_lo[d] = t.p_cnt[d] = 0;
+            tiles[b] = t;
+        }
+        return;
+    }
     // the last row whose base is <= b (rows without tiles share their successor's base and are skipped over)
     const uint32_t r = (uint32_t)last_le(tile_base, (int)g.own_rows, b);
     const uint32_t row = g.own_row0 + r;

@@ -130,19 +130,21 @@ struct PsimStepper {
     bool nbr_stale = true;                // nbr[cur_pos] does not match pos[cur_pos] / the current scale
     uint32_t* cell_id = nullptr;
     TileDesc* tiles = nullptr;
+    bool tiles_stale = false;  // step_kernel's descriptors were not rebuilt by the last binning (step_kernel_c ran)
     uint32_t* cell_start = nullptr;  // cells + 1 (+ padding)
     uint32_t* pad_start = nullptr;   // cells + 1: prefix sum of the cell counts rounded up to even (step_float.cuh)
     uint2* couple_i0 = nullptr;      // per couple: (first particle | has-a-second << 31, cell)
     uint32_t* tile_base = nullptr;   // own_rows + 1: first tile of every owned row
     uint32_t* d_couple_tiles = nullptr;
     TileC* tiles_c = nullptr;
-    uint32_t tiles_c_cap = 0, n_tiles_c = 0;
+    uint32_t tiles_c_cap = 0, n_tiles_c = 0;  // n_tiles_c: the count the host last read (exact with slabs: read at every binning)
+    uint32_t tiles_c_launch = 0;              // CTAs a step launches: n_tiles_c plus a margin on a single slab (step_float.cuh)
     bool float_grid = false;         // the grid is fine enough for step_kernel_c's exact fp32 offsets
     bool float_path = false;         // ... and the metadata's physics has a step_kernel_c variant
     PhysF physf{};
     bool force_int_path = false;     // PSIM_FORCE_INT_PATH=1: step_kernel on every grid (A/B measurements, tests)
     uint32_t* cell_count = nullptr;  // cells
-    uint32_t* block_sum = nullptr;
+    uint2* block_sum = nullptr;      // per scan block: (particles, particles with every cell rounded up to even)
     uint32_t* rank_in_cell = nullptr;
     uint32_t* perm = nullptr;
     Particle* staging = nullptr;   // ingest buffer (wire-format records)
@@ -181,7 +183,7 @@ struct PsimStepper {
     uint32_t n_total = 0;  // with ghost rows
     uint32_t own_lo = 0, own_hi = 0, b_lo_end = 0, b_hi_start = 0;
     Source src{};          // candidates of the binning in flight
-    bool binning_is_ingest = false;
+    uint64_t migrants_sent = 0;  // particles handed to a neighbour slab by the re-bins so far
 
     uint32_t snapshot_n[2] = {0, 0};
     FrameMetadata snapshot_meta[2]{};
@@ -452,8 +454,16 @@ void launch_step_c(PsimStepper* s, const StepArgs& a) {
     StepArgsC ac;
     ac.couple_i0 = s->couple_i0;
     ac.tiles = s->tiles_c;
-    if (s->kernel_frac == kFracNone) step_kernel_c<KN, kFracNone><<<s->n_tiles_c, kCouples, 0, s->stream>>>(a, ac);
-    else step_kernel_c<KN, kFracPoly><<<s->n_tiles_c, kCouples, 0, s->stream>>>(a, ac);
+    ac.n_tiles = s->d_couple_tiles;
+    if (s->kernel_frac == kFracNone) step_kernel_c<KN, kFracNone><<<s->tiles_c_launch, kCouples, 0, s->stream>>>(a, ac);
+    else step_kernel_c<KN, kFracPoly><<<s->tiles_c_launch, kCouples, 0, s->stream>>>(a, ac);
+    if (s->nranks > 1) return;  // slabs launch exactly the tiles there are
+    // a single slab sized the launch from the count it last saw: whatever the last re-bin made beyond it
+    if (s->kernel_frac == kFracNone)
+        step_kernel_c_surplus<KN, kFracNone><<<kSurplusCtas, kCouples, 0, s->stream>>>(a, ac, s->tiles_c_launch);
+    else
+        step_kernel_c_surplus<KN, kFracPoly><<<kSurplusCtas, kCouples, 0, s->stream>>>(a, ac, s->tiles_c_launch);
+    s->launches += 1;
 }
 
 template <int KN, int FRAC>
@@ -637,23 +647,25 @@ int refresh_ghost_records(PsimStepper* s) {
 // Binning, phase by phase (every phase is run for all slabs of the team before the next one starts)
 // ------------------------------------------------------------------------------------------------
 
-// cell_start = exclusive scan of cell_count; total -> cell_start[cells]
+// cell_start = exclusive scan of cell_count; total -> cell_start[cells]. Fine grids: pad_start in the same pass (the
+// counts rounded up to even: couples of step_kernel_c), then the couples and the tiles of every owned row.
 int enqueue_scan(PsimStepper* s) {
     uint32_t cells = s->grid.cells;
     uint32_t blocks = div_up(cells, kScanBlock);
-    scan_reduce_kernel<false><<<blocks, kScanThreads, 0, s->stream>>>(s->cell_count, cells, s->block_sum);
-    scan_top_kernel<<<1, 1024, 0, s->stream>>>(s->block_sum, blocks, s->cell_start + cells);
-    scan_apply_kernel<false><<<blocks, kScanThreads, 0, s->stream>>>(s->cell_count, cells, s->block_sum, s->cell_start);
+    scan_reduce_kernel<<<blocks, kScanThreads, 0, s->stream>>>(s->cell_count, cells, s->block_sum);
+    scan_top_kernel<<<1, 1024, 0, s->stream>>>(s->block_sum, blocks, s->cell_start + cells,
+                                               s->float_grid ? s->pad_start + cells : nullptr);
+    if (s->float_grid)
+        scan_apply_kernel<true><<<blocks, kScanThreads, 0, s->stream>>>(s->cell_count, cells, s->block_sum, s->cell_start, s->pad_start);
+    else
+        scan_apply_kernel<false><<<blocks, kScanThreads, 0, s->stream>>>(s->cell_count, cells, s->block_sum, s->cell_start, nullptr);
     s->launches += 3;
-    if (s->float_grid) {  // pad_start: the same scan over the counts rounded up to even (step_float.cuh)
-        scan_reduce_kernel<true><<<blocks, kScanThreads, 0, s->stream>>>(s->cell_count, cells, s->block_sum);
-        scan_top_kernel<<<1, 1024, 0, s->stream>>>(s->block_sum, blocks, s->pad_start + cells);
-        scan_apply_kernel<true><<<blocks, kScanThreads, 0, s->stream>>>(s->cell_count, cells, s->block_sum, s->pad_start);
+    if (s->float_grid) {
         couple_build_kernel<<<div_up(cells, 256), 256, 0, s->stream>>>(s->cell_start, s->pad_start, cells, s->couple_i0);
         row_cut_kernel<false><<<div_up(s->grid.own_rows, 64), 64, 0, s->stream>>>(s->cell_start, s->pad_start, s->grid,
-                                                                                s->tile_base, s->tiles_c);
-        row_tiles_kernel<<<1, 1024, 0, s->stream>>>(s->grid, s->tile_base, s->d_couple_tiles);
-        s->launches += 6;
+                                                                                s->tile_base, s->tiles_c, s->tiles_c_cap);
+        row_tiles_kernel<<<1, 1024, 0, s->stream>>>(s->grid, s->tile_base, s->tiles_c_cap, s->d_couple_tiles);
+        s->launches += 3;
     }
     CK(cudaGetLastError());
     return PSIM_OK;
@@ -723,15 +735,41 @@ int bin_phase_scan(PsimStepper* s, bool need_counts) {
     if (rc) return rc;
     if (need_counts) {
         slab_counts_kernel<<<1, 32, 0, s->stream>>>(s->cell_start, s->grid, s->d_flags, s->d_couple_tiles,
-                                                    s->float_grid ? s->tile_base : nullptr, s->hdr, s->d_counts);
+                                                    s->float_grid ? s->tile_base : nullptr, s->hdr,
+                                                    s->src.strict ? s->mig_counters : nullptr, s->d_counts);
         s->launches += 1;
         CK(cudaGetLastError());
-        CK(cudaMemcpyAsync(s->h_counts, s->d_counts, 16 * sizeof(uint32_t), cudaMemcpyDeviceToHost, s->stream));
+        CK(cudaMemcpyAsync(s->h_counts, s->d_counts, 12 * sizeof(uint32_t), cudaMemcpyDeviceToHost, s->stream));  // [15]: check_halo_error
     }
     return PSIM_OK;
 }
 
-// Host: wait for the counts (the only host synchronisation of a re-bin, and only with slabs).
+// The host has read the tile count of step_kernel_c. With slabs it reads it at every binning and launches exactly that
+// many CTAs (the halo protocol numbers the boundary tiles). A single slab reads it when a scene is ingested and at
+// psim_sync, never inside a frame: the launch keeps a margin over the count last seen (a re-bin changes it by a few
+// tiles), the kernel takes the real count from device memory, and the bound moves only when the count has drifted, so
+// that captured frames (CUDA graphs) stay valid.
+void set_tile_count(PsimStepper* s, uint32_t count) {
+    s->n_tiles_c = count;
+    if (s->nranks > 1) {
+        s->tiles_c_launch = count;
+        return;
+    }
+    uint32_t want = std::min(s->tiles_c_cap, count + count / 32 + 64);
+    bool keep = s->tiles_c_launch >= std::min(s->tiles_c_cap, count + count / 128 + 16) && s->tiles_c_launch <= want + want / 8;
+    if (const char* env = getenv("PSIM_TILE_LAUNCH_CAP")) {  // tests: fewer CTAs than tiles, the surplus loop steps the rest
+        want = std::max(1u, std::min(want, (uint32_t)std::atoi(env)));
+        keep = false;
+    }
+    if (!keep && s->tiles_c_launch != want) {
+        drop_frame_graphs(s);  // the grid size is part of a captured launch
+        s->tiles_c_launch = want;
+        // CTAs behind the last tile must find empty descriptors (the next binning writes them itself)
+        if (want > count) cudaMemsetAsync(s->tiles_c + count, 0, sizeof(TileC) * (size_t)(want - count), s->stream);
+    }
+}
+
+// Host: wait for the counts (the only host synchronisation of a binning: at an ingest, and at every re-bin with slabs).
 int bin_phase_commit(PsimStepper* s) {
     CK(cudaStreamSynchronize(s->stream));
     const uint32_t* h = s->h_counts;
@@ -755,10 +793,11 @@ int bin_phase_commit(PsimStepper* s) {
     s->own_hi = h[3];
     s->n_total = h[4];
     s->n = owned;
+    s->migrants_sent += std::min(h[10], s->box_capacity) + std::min(h[11], s->box_capacity);
     if (s->float_grid) {
-        if (h[6] > s->tiles_c_cap)
-            return fail(s, PSIM_ECAPACITY, "internal: %u couple tiles, room for %u", h[6], s->tiles_c_cap);
-        s->n_tiles_c = h[6];
+        if (h[9])
+            return fail(s, PSIM_ECAPACITY, "internal: more couple tiles than the %u there is room for", s->tiles_c_cap);
+        set_tile_count(s, h[6]);
         s->tiles_lo = h[7];
         s->tile_hi0 = h[8];
     }
@@ -788,18 +827,35 @@ int bin_phase_place(PsimStepper* s, bool ingest, XferOp& op) {
     return PSIM_OK;
 }
 
+int enqueue_tile_desc(PsimStepper* s) {
+    uint32_t tiles = div_up(s->n, kTile);
+    if (tiles)
+        tile_desc_kernel<<<div_up(tiles, 128), 128, 0, s->stream>>>(s->cell_start, s->grid, s->own_lo, s->own_hi, s->tiles);
+    s->launches += 1;
+    s->tiles_stale = false;
+    CK(cudaGetLastError());
+    return PSIM_OK;
+}
+
 // Phase 5: staging descriptors of the step kernel's tiles.
 int bin_phase_tiles(PsimStepper* s) {
     uint32_t tiles = div_up(s->n, kTile);
     if (tiles == 0) return PSIM_OK;
-    tile_desc_kernel<<<div_up(tiles, 128), 128, 0, s->stream>>>(s->cell_start, s->grid, s->own_lo, s->own_hi, s->tiles);
-    s->launches += 1;
-    if (s->float_grid && s->n_tiles_c) {
+    // step_kernel's descriptors: built now where it is the kernel that runs, else when a step first needs them
+    s->tiles_stale = true;
+    if (!s->float_path) {
+        int rc = enqueue_tile_desc(s);
+        if (rc) return rc;
+    }
+    if (s->float_grid) {
         row_cut_kernel<true><<<div_up(s->grid.own_rows, 64), 64, 0, s->stream>>>(s->cell_start, s->pad_start, s->grid,
-                                                                               s->tile_base, s->tiles_c);
+                                                                               s->tile_base, s->tiles_c, s->tiles_c_cap);
         s->launches += 1;
-        tile_build_kernel<<<div_up(s->n_tiles_c, 128), 128, 0, s->stream>>>(s->cell_start, s->pad_start, s->tile_base,
-                                                                          s->couple_i0, s->grid, s->tiles_c);
+        // with slabs the host knows the count of this binning; a single slab covers whatever the count has become
+        const uint32_t upto = s->nranks > 1 ? s->n_tiles_c : s->tiles_c_cap;
+        tile_build_kernel<<<div_up(std::max(upto, 1u), 128), 128, 0, s->stream>>>(s->cell_start, s->pad_start, s->tile_base,
+                                                                                 s->d_couple_tiles, s->tiles_c_launch, s->couple_i0,
+                                                                                 s->grid, s->tiles_c);
         s->launches += 1;
     }
     CK(cudaGetLastError());
@@ -849,7 +905,7 @@ int team_bin(const Team& t, bool ingest, const Particle* records, uint32_t count
         if ((rc = bin_phase_count(s, src, ops[r]))) return rc;
     }
     if ((rc = team_exchange(t, ops))) return rc;
-    const bool need_counts = ingest || slabs || t.ranks[0]->float_grid;  // the couple tiles are counted on the device
+    const bool need_counts = ingest || slabs;  // a single slab's re-bin needs nothing back on the host
     for (int r = 0; r < t.count; ++r)
         if ((rc = bin_phase_scan(t.ranks[r], need_counts))) return rc;
     if (need_counts) {
@@ -895,6 +951,10 @@ int enqueue_step(PsimStepper* s) {
     a.ph = s->phys;
     a.pf = s->physf;
     a.nbr_in = a.nbr_out = nullptr;
+    if (!s->float_path && !s->compact_mode && s->tiles_stale) {  // new metadata took the fine grid to step_kernel
+        int rc = enqueue_tile_desc(s);
+        if (rc) return rc;
+    }
     if (s->float_path && !s->compact_mode) {
         if (s->nbr_stale)  // team_step rebuilds stale records before it enqueues a step
             return fail(s, PSIM_ESTATE, "internal: a step was enqueued on stale neighbour records");
@@ -1134,7 +1194,7 @@ int team_run_frame(const Team& t) {
 // buffers are current when the frame starts. New metadata or a new scene drops the cache.
 // ------------------------------------------------------------------------------------------------
 bool frame_graph_usable(const PsimStepper* s) {
-    return s->cfg.use_graph && s->nranks == 1 && !s->group && !s->float_grid && !s->timing &&
+    return s->cfg.use_graph && s->nranks == 1 && !s->group && !s->timing &&
            s->cfg.schedule == PSIM_SCHEDULE_REFERENCE && s->n > 0;
 }
 
@@ -1144,6 +1204,11 @@ void drop_frame_graphs(PsimStepper* s) {
 }
 
 int run_frame_with_graph(PsimStepper* s) {
+    {   // records made stale by new metadata are rebuilt once, outside the captured frame
+        PsimStepper* self = s;
+        int rc = team_refresh_stale_records(Team{&self, 1, nullptr});
+        if (rc) return rc;
+    }
     const uint32_t key = (uint32_t)s->cur_pos | (uint32_t)s->cur_vel << 1 | (uint32_t)s->cur_ty << 2;
     auto it = s->frame_graphs.find(key);
     if (it == s->frame_graphs.end()) {
@@ -1185,6 +1250,17 @@ int run_frame_with_graph(PsimStepper* s) {
 
 Team lone(PsimStepper* const* s) { return Team{s, 1, nullptr}; }
 
+// A single slab on a fine grid learns the tile count of its last re-bin when the host next waits for it anyway (the
+// stream is idle here).
+int refresh_tile_count(PsimStepper* s) {
+    if (s->nranks > 1 || !s->float_grid || !s->has_scene || s->compact_mode) return PSIM_OK;
+    uint32_t c[2] = {0, 0};
+    CK(cudaMemcpy(c, s->d_couple_tiles, sizeof c, cudaMemcpyDeviceToHost));
+    if (c[1]) return fail(s, PSIM_ECAPACITY, "internal: more couple tiles than the %u there is room for", s->tiles_c_cap);
+    set_tile_count(s, c[0]);
+    return PSIM_OK;
+}
+
 int check_lone(PsimStepper* s, const char* what) {
     if (s->group) return fail(s, PSIM_ESTATE, "%s: this stepper is a slab of a group; use the psim_group_* call", what);
     return PSIM_OK;
@@ -1206,15 +1282,29 @@ int snapshot_index(const PsimStepper* s, uint32_t age) {
     return (s->snap_latest - (int)age + s->nsnap) % s->nsnap;
 }
 
+// A step that gave up waiting for a neighbour's halo ran on stale ghost rows: snapshots taken since are not valid
+// frames. The flag is sticky in the slab's HaloHeader; `h_counts[15]` is the host's copy, fetched over the copy stream.
+int check_halo_error(PsimStepper* s) {
+    if (!s->push || !s->hdr) return PSIM_OK;
+    if (s->h_counts[15]) {
+        s->failed = true;
+        return fail(s, PSIM_ECUDA, "slab %d: a step waited 20 s for a neighbour's halo (did a neighbour rank die?); "
+                    "the frames since are invalid", s->rank);
+    }
+    return PSIM_OK;
+}
+
 // Copy one of this slab's packed snapshots to `out` (host); waits only for that snapshot.
 int download_records(PsimStepper* s, int k, Particle* out) {
     CK(cudaStreamWaitEvent(s->copy_stream, s->snapshot_ready[k], 0));
     if (s->snapshot_n[k])
         CK(cudaMemcpyAsync(out, s->snapshot[k], sizeof(Particle) * (size_t)s->snapshot_n[k], cudaMemcpyDeviceToHost,
                            s->copy_stream));
+    if (s->push && s->hdr)
+        CK(cudaMemcpyAsync(&s->h_counts[15], &s->hdr->error, sizeof(uint32_t), cudaMemcpyDeviceToHost, s->copy_stream));
     CK(cudaEventRecord(s->snapshot_consumed[k], s->copy_stream));
     CK(cudaStreamSynchronize(s->copy_stream));
-    return PSIM_OK;
+    return check_halo_error(s);
 }
 
 }  // namespace
@@ -1436,7 +1526,8 @@ int psim_create(const PsimConfig* config, PsimStepper** out) {
         CKC(cudaMemset(st->pad_start, 0, sizeof(uint32_t) * ((size_t)g.cells + 1 + kPadCells)));
         CKC(cudaMalloc(&st->couple_i0, sizeof(uint2) * couples));
         CKC(cudaMalloc(&st->tile_base, sizeof(uint32_t) * ((size_t)g.own_rows + 1)));
-        CKC(cudaMalloc(&st->d_couple_tiles, sizeof(uint32_t)));
+        CKC(cudaMalloc(&st->d_couple_tiles, 2 * sizeof(uint32_t)));  // [0] tiles of the last binning, [1] sticky: they did not fit
+        CKC(cudaMemset(st->d_couple_tiles, 0, 2 * sizeof(uint32_t)));
         CKC(cudaMalloc(&st->tiles_c, sizeof(TileC) * (size_t)st->tiles_c_cap));
         for (int k = 0; k < 2; ++k) {
             CKC(cudaMalloc(&st->nbr[k], sizeof(float4) * (cap_total + kPadParticles)));
@@ -1444,7 +1535,7 @@ int psim_create(const PsimConfig* config, PsimStepper** out) {
         }
     }
     CKC(cudaMalloc(&st->cell_count, sizeof(uint32_t) * (size_t)g.cells));
-    CKC(cudaMalloc(&st->block_sum, sizeof(uint32_t) * (size_t)div_up(g.cells, kScanBlock)));
+    CKC(cudaMalloc(&st->block_sum, sizeof(uint2) * (size_t)div_up(g.cells, kScanBlock)));
     CKC(cudaMalloc(&st->rank_in_cell, sizeof(uint32_t) * cand_cap));
     CKC(cudaMalloc(&st->perm, sizeof(uint32_t) * cap_total));
     CKC(cudaMalloc(&st->cell_id, sizeof(uint32_t) * cap_total));
@@ -1459,6 +1550,7 @@ int psim_create(const PsimConfig* config, PsimStepper** out) {
     CKC(cudaMalloc(&st->d_flags, sizeof(uint32_t)));
     CKC(cudaMalloc(&st->d_counts, 16 * sizeof(uint32_t)));
     CKC(cudaMallocHost(&st->h_counts, 16 * sizeof(uint32_t)));
+    std::memset(st->h_counts, 0, 16 * sizeof(uint32_t));
     CKC(cudaMemset(st->cell_start, 0, sizeof(uint32_t) * ((size_t)g.cells + 1 + kPadCells)));
     CKC(cudaMemset(st->d_flags, 0, sizeof(uint32_t)));
 #undef CKC
@@ -1730,6 +1822,12 @@ int psim_upload_staged(PsimStepper* s) {
 
 int psim_set_metadata(PsimStepper* s, const FrameMetadata* meta) {
     if (!s || !meta) return PSIM_EINVAL;
+    // The reference switches between its two layouts on every frame's metadata (kernel.cuh:143-150); here the layout is
+    // the one the scene was uploaded in (the all-pairs mode keeps the input order, the grid mode is cell-sorted), so a
+    // header-only update that flips data_structure is refused rather than silently ignored: upload the scene again.
+    if (s->has_scene && (meta->data_structure == 0) != s->compact_mode)
+        return fail(s, PSIM_EINVAL, "psim_set_metadata: data_structure %u does not match the layout the scene was uploaded in (%s); "
+                    "upload the scene again to switch", meta->data_structure, s->compact_mode ? "CompactArray" : "MatrixBuckets");
     apply_metadata(s, *meta);  // captured by value at the next enqueue, like kernel_bucket.cuh:121
     return PSIM_OK;
 }
@@ -1803,6 +1901,8 @@ int psim_sync(PsimStepper* s) {
         if (halo_error)
             return fail(s, PSIM_ECUDA, "slab %d: a step waited 20 s for a neighbour's halo (did a neighbour rank die?)", s->rank);
     }
+    int rc = refresh_tile_count(s);
+    if (rc) return rc;
     if (s->timing) return collect_timing(s);
     return PSIM_OK;
 }
@@ -1840,6 +1940,8 @@ int psim_download_frame_begin(PsimStepper* s, uint32_t age, FrameHeader* dst) {
     if (s->snapshot_n[k])
         CK(cudaMemcpyAsync(dst->particles, s->snapshot[k], sizeof(Particle) * (size_t)s->snapshot_n[k],
                            cudaMemcpyDeviceToHost, s->copy_stream));
+    if (s->push && s->hdr)
+        CK(cudaMemcpyAsync(&s->h_counts[15], &s->hdr->error, sizeof(uint32_t), cudaMemcpyDeviceToHost, s->copy_stream));
     CK(cudaEventRecord(s->snapshot_consumed[k], s->copy_stream));
     write_header(dst, s->snapshot_meta[k], s->snapshot_n[k]);  // the header is host data: valid at once
     s->pending_dst = dst;
@@ -1853,7 +1955,7 @@ int psim_download_frame_end(PsimStepper* s) {
     CK(cudaSetDevice(s->device));
     s->pending_dst = nullptr;
     CK(cudaStreamSynchronize(s->copy_stream));
-    return PSIM_OK;
+    return check_halo_error(s);
 }
 
 void* psim_host_alloc(size_t bytes) {
@@ -1874,6 +1976,7 @@ uint64_t psim_steps_executed(const PsimStepper* s) { return s ? s->steps_execute
 uint64_t psim_rebins_executed(const PsimStepper* s) { return s ? s->rebins_executed : 0; }
 uint64_t psim_kernel_launches(const PsimStepper* s) { return s ? s->launches : 0; }
 uint32_t psim_cell_count(const PsimStepper* s) { return s ? s->grid.cells : 0; }
+uint64_t psim_migrants_sent(const PsimStepper* s) { return s ? s->migrants_sent : 0; }
 
 int psim_get_cell_start(PsimStepper* s, uint32_t* out) {
     if (!s || !out) return PSIM_EINVAL;
@@ -1918,6 +2021,8 @@ int psim_tile_stats(PsimStepper* s, PsimTileStats* out) {
         return PSIM_OK;
     }
     out->float_path = s->float_path ? 1u : 0u;
+    int rc = refresh_tile_count(s);
+    if (rc) return rc;
     if (s->float_path) {
         std::vector<TileC> t(s->n_tiles_c);
         if (!t.empty()) CK(cudaMemcpy(t.data(), s->tiles_c, sizeof(TileC) * t.size(), cudaMemcpyDeviceToHost));
@@ -1953,21 +2058,15 @@ int psim_device_state(PsimStepper* s, const void** pos, const void** vel, const 
     return PSIM_OK;
 }
 
-int psim_balance_rows(const FrameHeader* scene, uint32_t grid_y_log2, uint32_t slab_count, uint32_t* bounds) {
+int psim_balance_rows_hist(const uint64_t* row_counts, uint32_t grid_y_log2, uint32_t slab_count, uint32_t* bounds) {
     PsimStepper* s = nullptr;
-    if (!scene || !bounds || slab_count == 0 || grid_y_log2 < 3 || grid_y_log2 > 15 || (2ull * slab_count) > (1ull << grid_y_log2))
+    if (!row_counts || !bounds || slab_count == 0 || grid_y_log2 < 3 || grid_y_log2 > 15 || (2ull * slab_count) > (1ull << grid_y_log2))
         return fail(s, PSIM_EINVAL, "psim_balance_rows: bad argument (every slab needs 2 of the %llu cell rows)",
                     1ull << (grid_y_log2 & 31));
     const uint32_t rows = 1u << grid_y_log2;
     std::vector<uint64_t> upto(rows + 1, 0);  // live particles in rows < r
-    const Particle* p = scene->particles;
-    uint64_t live = 0;
-    for (uint32_t i = 0; i < scene->particle_count; ++i)
-        if (p[i].ty >= 0) {
-            upto[(p[i].y >> (32 - grid_y_log2)) + 1] += 1;
-            live += 1;
-        }
-    for (uint32_t r = 0; r < rows; ++r) upto[r + 1] += upto[r];
+    for (uint32_t r = 0; r < rows; ++r) upto[r + 1] = upto[r] + row_counts[r];
+    const uint64_t live = upto[rows];
     bounds[0] = 0;
     bounds[slab_count] = rows;
     for (uint32_t k = 1; k < slab_count; ++k) {
@@ -1980,6 +2079,17 @@ int psim_balance_rows(const FrameHeader* scene, uint32_t grid_y_log2, uint32_t s
     for (uint32_t k = 1; k < slab_count; ++k) bounds[k] = std::max(bounds[k], bounds[k - 1] + 2);
     for (uint32_t k = slab_count - 1; k >= 1; --k) bounds[k] = std::min(bounds[k], bounds[k + 1] - 2);
     return PSIM_OK;
+}
+
+int psim_balance_rows(const FrameHeader* scene, uint32_t grid_y_log2, uint32_t slab_count, uint32_t* bounds) {
+    PsimStepper* s = nullptr;
+    if (!scene || grid_y_log2 < 3 || grid_y_log2 > 15)
+        return fail(s, PSIM_EINVAL, "psim_balance_rows: bad argument");
+    std::vector<uint64_t> hist((size_t)1 << grid_y_log2, 0);
+    const Particle* p = scene->particles;
+    for (uint32_t i = 0; i < scene->particle_count; ++i)
+        if (p[i].ty >= 0) hist[p[i].y >> (32 - grid_y_log2)] += 1;
+    return psim_balance_rows_hist(hist.data(), grid_y_log2, slab_count, bounds);
 }
 
 void psim_slab_bounds_of(const uint32_t* bounds, uint32_t slab_rank, uint32_t slab_count, uint32_t out[4]) {

@@ -53,3 +53,54 @@ def reduce_scalar(dist, value: float, op: str = "max", device=None) -> float:
     t = torch.tensor([value], dtype=torch.float64, device=device)
     dist.all_reduce(t, op={"max": dist.ReduceOp.MAX, "sum": dist.ReduceOp.SUM, "min": dist.ReduceOp.MIN}[op])
     return float(t.item())
+
+
+def rebalance_across_ranks(dist, st, make_stepper, device=None):
+    """Move the slab boundaries of a running one-process-per-GPU decomposition to where the particles are now
+    (BASELINE.json configs[4]). Collective over `dist`, called between two frames:
+
+      1. every rank snapshots and downloads its own particles and histograms them by global cell row;
+      2. the histograms are summed over the ranks (one all-reduce) and every rank cuts the same boundaries
+         (psim_balance_rows_hist: equal shares of the particles, every slab at least 2 rows);
+      3. every rank sends each of its particles to the rank that owns its row now (all-to-all over the records,
+         20 bytes each; slabs are bands of rows, so almost everything stays where it is);
+      4. the stepper is re-created on the new rows (`make_stepper(bounds)` must return a new, communicator-initialised
+         Stepper: the slab geometry is fixed at psim_create) and takes the records in as a scene.
+
+    Like SlabGroup.rebalance this restarts the step / re-bin schedule (an upload's worth of work, for when the imbalance
+    has grown). The received records arrive in ascending source rank = ascending row order, each rank's in its sorted
+    order, so the ingest's stable sort reproduces the cell-sorted order a single slab would have.
+    Returns (new stepper, boundaries)."""
+    import torch
+
+    from .frame import PARTICLE_DTYPE, FrameBuffer
+    from .stepper import balance_rows_hist
+
+    world, rank = dist.get_world_size(), dist.get_rank()
+    ly = st.grid_log2[1]
+    meta = st.get_metadata()
+    st.sync()
+    st.snapshot_async()
+    mine = st.download().particles
+    rows = (mine["y"] >> np.uint32(32 - ly)).astype(np.int64)
+    hist = torch.from_numpy(np.bincount(rows, minlength=1 << ly).astype(np.int64)).to(device)
+    dist.all_reduce(hist)
+    bounds = balance_rows_hist(hist.cpu().numpy().astype(np.uint64), ly, world)
+    owner = np.searchsorted(np.asarray(bounds[1:-1], dtype=np.int64), rows, side="right")
+    order = np.argsort(owner, kind="stable")
+    send_counts = np.bincount(owner, minlength=world).astype(np.int64)
+    send = torch.from_numpy(np.ascontiguousarray(mine[order]).view(np.uint8).reshape(-1).copy()).to(device)
+    counts_dev = torch.from_numpy(send_counts).to(device)
+    recv_counts_dev = torch.zeros_like(counts_dev)
+    dist.all_to_all_single(recv_counts_dev, counts_dev)
+    recv_counts = recv_counts_dev.cpu().numpy()
+    recv = torch.empty(int(recv_counts.sum()) * 20, dtype=torch.uint8, device=device)
+    dist.all_to_all_single(recv, send, output_split_sizes=(recv_counts * 20).tolist(),
+                           input_split_sizes=(send_counts * 20).tolist())
+    records = recv.cpu().numpy().view(PARTICLE_DTYPE)
+    st.close()
+    new = make_stepper(bounds)
+    fb = FrameBuffer(max(len(records), 1), meta)
+    fb.set_particles(records)
+    new.upload(fb)
+    return new, bounds

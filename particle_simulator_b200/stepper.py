@@ -112,6 +112,7 @@ def lib() -> ctypes.CDLL:
             "psim_comm_init": [vp, vp],
             "psim_group_create": [ctypes.POINTER(vp), ctypes.c_uint32, ctypes.POINTER(vp)],
             "psim_balance_rows": [vp, ctypes.c_uint32, ctypes.c_uint32, ctypes.POINTER(ctypes.c_uint32)],
+            "psim_balance_rows_hist": [vp, ctypes.c_uint32, ctypes.c_uint32, ctypes.POINTER(ctypes.c_uint32)],
             "psim_group_upload_frame": [vp, vp],
             "psim_group_set_metadata": [vp, vp],
             "psim_group_run_frame_async": [vp],
@@ -121,6 +122,8 @@ def lib() -> ctypes.CDLL:
             "psim_group_sync": [vp],
             "psim_group_download_frame": [vp, vp],
         }.items():
+            if os.environ.get("PSIM_LIB") and not hasattr(L, name):
+                continue  # an older build of the library under A/B test (tools/ab_step.py) lacks the newest entry points
             getattr(L, name).restype = ctypes.c_int
             getattr(L, name).argtypes = args
         L.psim_group_destroy.restype = None
@@ -133,10 +136,12 @@ def lib() -> ctypes.CDLL:
         L.psim_halo_mode.argtypes = [vp]
         L.psim_particle_count.restype = ctypes.c_uint32
         L.psim_cell_count.restype = ctypes.c_uint32
-        for name in ("psim_steps_executed", "psim_rebins_executed", "psim_kernel_launches"):
+        for name in ("psim_steps_executed", "psim_rebins_executed", "psim_kernel_launches", "psim_migrants_sent"):
+            if name == "psim_migrants_sent" and os.environ.get("PSIM_LIB") and not hasattr(L, name):
+                continue  # an older build of the library under A/B test (tools/ab_step.py)
             getattr(L, name).restype = ctypes.c_uint64
-        for name in ("psim_particle_count", "psim_cell_count", "psim_steps_executed", "psim_rebins_executed",
-                     "psim_kernel_launches"):
+            getattr(L, name).argtypes = [vp]
+        for name in ("psim_particle_count", "psim_cell_count"):
             getattr(L, name).argtypes = [vp]
         _lib = L
     return _lib
@@ -309,6 +314,11 @@ class Stepper:
     def kernel_launches(self) -> int:
         return int(lib().psim_kernel_launches(self._h))
 
+    @property
+    def migrants_sent(self) -> int:
+        """Particles this slab has handed to its neighbours at re-bins so far."""
+        return int(lib().psim_migrants_sent(self._h))
+
     def cell_start(self) -> np.ndarray:
         out = np.zeros(self.cell_count + 1, dtype=np.uint32)
         self._check(lib().psim_get_cell_start(self._h, ctypes.c_void_p(out.ctypes.data)))
@@ -330,6 +340,17 @@ def balance_rows(frame: FrameBuffer, grid_y_log2: int, slab_count: int) -> list[
     rc = lib().psim_balance_rows(frame.ptr, grid_y_log2, slab_count, out)
     if rc != 0:
         raise PsimError(f"psim_balance_rows failed ({rc}): {lib().psim_last_error(None).decode()}")
+    return list(out)
+
+
+def balance_rows_hist(row_counts: np.ndarray, grid_y_log2: int, slab_count: int) -> list[int]:
+    """psim_balance_rows_hist: the same cut from a histogram of live particles per global cell row."""
+    hist = np.ascontiguousarray(row_counts, dtype=np.uint64)
+    assert hist.size == 1 << grid_y_log2
+    out = (ctypes.c_uint32 * (slab_count + 1))()
+    rc = lib().psim_balance_rows_hist(ctypes.c_void_p(hist.ctypes.data), grid_y_log2, slab_count, out)
+    if rc != 0:
+        raise PsimError(f"psim_balance_rows_hist failed ({rc}): {lib().psim_last_error(None).decode()}")
     return list(out)
 
 

@@ -74,6 +74,15 @@ def test_null_records_are_dropped_in_place_and_frames_run_exactly_s_steps():
         st.run_frame_async()
         st.sync()
         assert st.rebins_executed == 1
+        # a header-only update cannot switch the layout of a scene that is already there (include/psim_b200.h)
+        from particle_simulator_b200.stepper import PsimError
+
+        flipped = fb.metadata.copy()
+        flipped["data_structure"] = COMPACT_ARRAY
+        with pytest.raises(PsimError, match="data_structure"):
+            st.set_metadata(flipped)
+        assert int(st.get_metadata()["data_structure"]) == 1
+        st.set_metadata(fb.metadata)  # the same layout: accepted
 
 
 def test_all_pairs_cannot_be_decomposed_into_slabs():

@@ -240,3 +240,52 @@ def test_metadata_updates_between_steps_rebuild_the_neighbour_records():
         dy = np.abs((g["y"].astype(np.int64) - wnt["y"].astype(np.int64) + 2**31) % 2**32 - 2**31)
         assert max(dx.max(), dy.max()) <= 64 * 3 * (k + 1), (k, dx.max(), dy.max())
         assert np.allclose(g["vx"], wnt["vx"], rtol=1e-3, atol=0.05) and np.allclose(g["vy"], wnt["vy"], rtol=1e-3, atol=0.05)
+
+
+def test_frames_on_fine_grids_do_not_wait_for_the_host_and_replay_as_graphs():
+    """A single slab's re-bin leaves the tile count in device memory: psim_run_frame_async returns without waiting for
+    the frame (the reference's compute_frame wanted exactly that, cuda_simulator.cu:7-26), frames can be captured as
+    CUDA graphs on fine grids too, and a launch smaller than the tile count (PSIM_TILE_LAUNCH_CAP: the count outgrew
+    the host's margin) still steps every tile. All bit-identical."""
+    import time
+
+    from particle_simulator_b200.stepper import Stepper
+
+    grid = (10, 10)
+    fb = boxed(500 * 500, grid)
+    w = float(fb.metadata["box_width"])
+    io.scene_hex_square(fb, 500, 500, (0.45 * w, 0.52 * w), 1.05, 150.0, 250.0, 0, seed=29)
+    fb.metadata["step_dt"] = 20e-15
+    fb.metadata["steps_per_frame"] = 100
+
+    def run(use_graph: bool, launch_cap: int | None = None):
+        if launch_cap:
+            os.environ["PSIM_TILE_LAUNCH_CAP"] = str(launch_cap)
+        try:
+            with Stepper(grid, fb.count, use_graph=use_graph) as st:
+                st.upload(fb)
+                assert st.tile_stats()["float_path"] == 1
+                frames, enqueue, total = [], [], []
+                for _ in range(4):
+                    st.sync()
+                    t0 = time.perf_counter()
+                    st.run_frame_async()
+                    t1 = time.perf_counter()
+                    st.sync()
+                    t2 = time.perf_counter()
+                    enqueue.append(t1 - t0)
+                    total.append(t2 - t0)
+                    frames.append(st.download().particles.copy())
+                assert (st.steps_executed, st.rebins_executed) == (404, 24)
+                return frames, enqueue, total
+        finally:
+            os.environ.pop("PSIM_TILE_LAUNCH_CAP", None)
+
+    plain, enq_plain, tot_plain = run(False)
+    graph, enq_graph, tot_graph = run(True)
+    capped, _, _ = run(False, launch_cap=7)
+    for a, b, c in zip(plain, graph, capped):
+        assert a.tobytes() == b.tobytes() == c.tobytes()
+    print(f"frame {1e3 * min(tot_plain):.2f} ms; enqueue {1e3 * min(enq_plain):.2f} ms launch by launch, "
+          f"{1e3 * min(enq_graph[1:]):.3f} ms as a graph")
+    assert min(enq_graph[1:]) < 0.25 * min(tot_graph)  # the host is free while the frame runs

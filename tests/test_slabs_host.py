@@ -117,3 +117,70 @@ def test_gloo_world_size_2(tmp_path):
     port = _free_port()
     mp.spawn(_gloo_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
     assert sorted(os.listdir(tmp_path)) == ["ok0", "ok1"]
+
+
+class _HostSlab:
+    """Stands in for a Stepper in the gloo test of slabs.rebalance_across_ranks: holds records, no GPU."""
+
+    def __init__(self, grid_log2, meta, particles=None):
+        self.grid_log2, self._meta = grid_log2, meta
+        self.particles = particles
+        self.closed = False
+
+    def get_metadata(self):
+        return self._meta
+
+    def sync(self):
+        pass
+
+    def snapshot_async(self):
+        pass
+
+    def download(self):
+        fb = FrameBuffer(max(len(self.particles), 1), self._meta)
+        fb.set_particles(self.particles)
+        return fb
+
+    def upload(self, frame):
+        self.particles = frame.particles.copy()
+
+    def close(self):
+        self.closed = True
+
+
+def _rebalance_worker(rank: int, world: int, port: int, out_dir: str) -> None:
+    import torch.distributed as dist
+
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        w = workloads.clustered_mixed((8, 8), clusters=4, side=30, gas=2000, seed=5)
+        p = w.frame.particles
+        p = p[np.argsort(p["y"] >> np.uint32(24), kind="stable")]  # rows ascending, like a cell-sorted state
+        mine = slabs.split_by_slab(p, world, 8)[rank]              # equal rows: lopsided
+        old = _HostSlab((8, 8), w.frame.metadata, mine)
+        made = {}
+
+        def make(bounds):
+            made["bounds"] = list(bounds)
+            return _HostSlab((8, 8), w.frame.metadata)
+
+        new, bounds = slabs.rebalance_across_ranks(dist, old, make)
+        assert old.closed and bounds == made["bounds"]
+        from particle_simulator_b200.stepper import balance_rows
+
+        assert bounds == balance_rows(w.frame, 8, world)  # the cut from the all-reduced histogram = the cut of the scene
+        want = slabs.split_by_slab(p, world, 8, bounds)[rank]
+        assert new.particles.tobytes() == want.tobytes()  # every record reached the owner of its row, order kept
+        open(os.path.join(out_dir, f"ok{rank}"), "w").write(str(len(want)))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_rebalance_across_ranks_routes_records_to_their_new_owners(tmp_path):
+    import torch.multiprocessing as mp
+
+    port = _free_port()
+    mp.spawn(_rebalance_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    held = [int(open(os.path.join(tmp_path, f"ok{r}")).read()) for r in range(2)]
+    assert max(held) / (sum(held) / 2) < 1.1, held

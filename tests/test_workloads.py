@@ -41,28 +41,42 @@ def test_slab_crystal_rows_partition_the_crystal():
 
 
 def test_presets_round_trip_a_scene():
-    """Preset::{from_frame, to_frame} and the Presets list (particle_io/src/presets.rs:84-154)."""
+    """Preset::{from_frame, to_frame} and the Presets list (particle_io/src/presets.rs:84-154) through the C ABI of
+    include/psim_scene.h (psim_presets_*, psim_preset_*)."""
+    import pytest
+
     from particle_simulator_b200 import io
     from particle_simulator_b200.frame import FrameBuffer, default_metadata
-    from particle_simulator_b200.presets import Preset, Presets
+    from particle_simulator_b200.presets import Presets
 
     fb = FrameBuffer(40)
     fb.metadata["box_width"], fb.metadata["box_height"] = 30e-9, 20e-9
     fb.metadata["particles"][1] = (3.2e-10, 0.9e-21, 11.0, 5.0)
     fb.metadata["steps_per_frame"] = 7  # not part of a preset
     io.scene_hex_square(fb, 5, 4, (15e-9, 10e-9), 1.0, 5.0, 5.0, 1, seed=1)
-    p = Preset.from_frame("droplet", fb)
+    lib = Presets()
+    assert lib.get_presets_len() == 0
+    assert lib.add_preset("droplet", fb) == 0
+    p = lib.get_preset(0)
+    assert p.name == "droplet" and p.particle_count == 20
     back = p.to_frame()
     assert back.count == 20 and back.particles.tobytes() == fb.particles.tobytes()
     assert float(back.metadata["box_width"]) == np.float32(30e-9) and float(back.metadata["box_height"]) == np.float32(20e-9)
     assert back.metadata["particles"].tobytes() == fb.metadata["particles"].tobytes()
-    assert int(back.metadata["steps_per_frame"]) == int(default_metadata()["steps_per_frame"])
-    lib = Presets()
-    lib.add_preset(p)
-    lib.add_preset(Preset.from_frame("again", back))
+    assert int(back.metadata["steps_per_frame"]) == int(default_metadata()["steps_per_frame"])  # a new frame's default
+    assert lib.add_preset("again", back) == 1
     assert lib.get_presets_len() == 2 and lib.get_preset(1).name == "again"
-    lib.change_preset(p, 5)  # past the end: ignored
-    lib.change_preset(Preset.from_frame("renamed", back), 0)
-    assert lib.get_preset(0).name == "renamed"
+    lib.change_preset("ignored", fb, 5)  # past the end: ignored (presets.rs:147-152)
+    assert lib.get_presets_len() == 2
+    empty = FrameBuffer(1)
+    lib.change_preset("renamed", empty, 0)
+    assert lib.get_preset(0).name == "renamed" and lib.get_preset(0).particle_count == 0
+    assert lib.get_preset(0).to_frame().count == 0
+    assert lib.duplicate_preset(1, "copy") == 2 and lib.get_preset(2).to_frame().particles.tobytes() == fb.particles.tobytes()
     lib.delete_preset(0)
-    assert lib.get_presets_len() == 1 and lib.get_preset(0).name == "again"
+    assert lib.get_presets_len() == 2 and lib.get_preset(0).name == "again" and lib.get_preset(1).name == "copy"
+    with pytest.raises(IndexError):
+        lib.delete_preset(7)
+    with pytest.raises(IndexError):
+        lib.get_preset(2)
+    lib.close()
