@@ -349,8 +349,9 @@ __global__ void row_cut_kernel(const uint32_t* __restrict__ cell_start, const ui
 
 // Tiles of every owned row (row_cut_kernel<false> left the counts in tile_base); single block: exclusive scan in place
 // into tile_base[0..own_rows]; total (at most the room in the tile table) -> total_out[0], total_out[1] |= it was more.
+// `host_mirror`: the same two words in mapped host memory (the host reads them at its next wait, without a copy).
 __global__ void __launch_bounds__(1024) row_tiles_kernel(Grid g, uint32_t* __restrict__ tile_base, uint32_t tiles_cap,
-                                                         uint32_t* __restrict__ total_out) {
+                                                         uint32_t* __restrict__ total_out, uint32_t* __restrict__ host_mirror) {
     __shared__ uint32_t warp_sum[32];
     __shared__ uint32_t carry;
     if (threadIdx.x == 0) carry = 0;
@@ -385,6 +386,8 @@ __global__ void __launch_bounds__(1024) row_tiles_kernel(Grid g, uint32_t* __res
         tile_base[g.own_rows] = carry;
         total_out[0] = min(carry, tiles_cap);
         if (carry > tiles_cap) total_out[1] = 1u;
+        host_mirror[0] = min(carry, tiles_cap);
+        host_mirror[1] = total_out[1];
     }
 }
 

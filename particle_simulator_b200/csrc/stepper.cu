@@ -87,6 +87,7 @@ struct FrameGraph {  // one captured frame (run_frame_with_graph)
     cudaGraphExec_t exec = nullptr;
     uint64_t steps = 0, rebins = 0, launches = 0;
     int end_pos = 0, end_vel = 0, end_ty = 0;
+    uint32_t n = 0, n_total = 0, tiles_launch = 0;  // what the captured launches were sized for
 };
 
 struct PsimStepper {
@@ -177,7 +178,8 @@ struct PsimStepper {
     uint32_t tiles_lo = 0, tile_hi0 = 0;  // couple tiles of the first owned row: [0, tiles_lo); of the last: [tile_hi0, ..)
     uint32_t* d_flags = nullptr;   // 1
     uint32_t* d_counts = nullptr;  // 16
-    uint32_t* h_counts = nullptr;  // pinned, 16
+    uint32_t* h_counts = nullptr;  // pinned and mapped, 16: [0..11] written by slab_counts_kernel, [12..13] by row_tiles_kernel, [15] check_halo_error
+    uint32_t* h_counts_dev = nullptr;  // the device's address of h_counts
 
     uint32_t n = 0;        // particles this stepper owns
     uint32_t n_total = 0;  // with ghost rows
@@ -426,12 +428,14 @@ bool make_phys_f(const FrameMetadata& m, const Phys& ph, const Grid& g, int kn, 
 }
 
 void apply_metadata(PsimStepper* s, const FrameMetadata& m) {
+    // the same metadata again (a scene re-uploaded every frame by a pipelined host): captured frames stay valid
+    const bool same = s->has_scene && std::memcmp(&s->meta, &m, sizeof m) == 0;
     s->meta = m;
     s->phys = make_phys(m, &s->kernel_kn, &s->kernel_frac, &s->kernel_aniso);
     s->float_path = s->float_grid && !s->force_int_path &&
                     make_phys_f(m, s->phys, s->grid, s->kernel_kn, s->kernel_frac, &s->physf);
     s->nbr_stale = true;  // the records carry the old scale (or were not kept at all): rebuilt before the next step
-    drop_frame_graphs(s);  // captured launches carry the old constants
+    if (!same) drop_frame_graphs(s);  // captured launches carry the old constants
 }
 
 template <int KN, int FRAC>
@@ -664,7 +668,8 @@ int enqueue_scan(PsimStepper* s) {
         couple_build_kernel<<<div_up(cells, 256), 256, 0, s->stream>>>(s->cell_start, s->pad_start, cells, s->couple_i0);
         row_cut_kernel<false><<<div_up(s->grid.own_rows, 64), 64, 0, s->stream>>>(s->cell_start, s->pad_start, s->grid,
                                                                                 s->tile_base, s->tiles_c, s->tiles_c_cap);
-        row_tiles_kernel<<<1, 1024, 0, s->stream>>>(s->grid, s->tile_base, s->tiles_c_cap, s->d_couple_tiles);
+        row_tiles_kernel<<<1, 1024, 0, s->stream>>>(s->grid, s->tile_base, s->tiles_c_cap, s->d_couple_tiles,
+                                                    s->h_counts_dev + 12);
         s->launches += 3;
     }
     CK(cudaGetLastError());
@@ -734,12 +739,14 @@ int bin_phase_scan(PsimStepper* s, bool need_counts) {
     int rc = enqueue_scan(s);
     if (rc) return rc;
     if (need_counts) {
+        // The counts go straight into page-locked host memory (mapped: the kernel stores over PCIe), not through a
+        // device-to-host copy: a copy engine may be busy for milliseconds with the previous frame's snapshot on its way
+        // out, and these 48 bytes would queue behind it while the whole stream waits.
         slab_counts_kernel<<<1, 32, 0, s->stream>>>(s->cell_start, s->grid, s->d_flags, s->d_couple_tiles,
                                                     s->float_grid ? s->tile_base : nullptr, s->hdr,
-                                                    s->src.strict ? s->mig_counters : nullptr, s->d_counts);
+                                                    s->src.strict ? s->mig_counters : nullptr, s->h_counts_dev);
         s->launches += 1;
         CK(cudaGetLastError());
-        CK(cudaMemcpyAsync(s->h_counts, s->d_counts, 12 * sizeof(uint32_t), cudaMemcpyDeviceToHost, s->stream));  // [15]: check_halo_error
     }
     return PSIM_OK;
 }
@@ -755,8 +762,8 @@ void set_tile_count(PsimStepper* s, uint32_t count) {
         s->tiles_c_launch = count;
         return;
     }
-    uint32_t want = std::min(s->tiles_c_cap, count + count / 32 + 64);
-    bool keep = s->tiles_c_launch >= std::min(s->tiles_c_cap, count + count / 128 + 16) && s->tiles_c_launch <= want + want / 8;
+    uint32_t want = std::min(s->tiles_c_cap, count + count / 64 + 32);
+    bool keep = s->tiles_c_launch >= std::min(s->tiles_c_cap, count + count / 256 + 8) && s->tiles_c_launch <= want + want / 16;
     if (const char* env = getenv("PSIM_TILE_LAUNCH_CAP")) {  // tests: fewer CTAs than tiles, the surplus loop steps the rest
         want = std::max(1u, std::min(want, (uint32_t)std::atoi(env)));
         keep = false;
@@ -1211,6 +1218,12 @@ int run_frame_with_graph(PsimStepper* s) {
     }
     const uint32_t key = (uint32_t)s->cur_pos | (uint32_t)s->cur_vel << 1 | (uint32_t)s->cur_ty << 2;
     auto it = s->frame_graphs.find(key);
+    if (it != s->frame_graphs.end() && (it->second.n != s->n || it->second.n_total != s->n_total ||
+                                        it->second.tiles_launch != s->tiles_c_launch)) {
+        cudaGraphExecDestroy(it->second.exec);  // another scene since: the launches were sized for other counts
+        s->frame_graphs.erase(it);
+        it = s->frame_graphs.end();
+    }
     if (it == s->frame_graphs.end()) {
         const uint64_t steps0 = s->steps_executed, rebins0 = s->rebins_executed, launches0 = s->launches;
         CK(cudaStreamBeginCapture(s->stream, cudaStreamCaptureModeThreadLocal));
@@ -1233,6 +1246,9 @@ int run_frame_with_graph(PsimStepper* s) {
         fg.end_pos = s->cur_pos;
         fg.end_vel = s->cur_vel;
         fg.end_ty = s->cur_ty;
+        fg.n = s->n;
+        fg.n_total = s->n_total;
+        fg.tiles_launch = s->tiles_c_launch;
         s->frame_graphs[key] = fg;
         CK(cudaGraphLaunch(fg.exec, s->stream));  // the capture executed nothing
         return PSIM_OK;
@@ -1254,8 +1270,7 @@ Team lone(PsimStepper* const* s) { return Team{s, 1, nullptr}; }
 // stream is idle here).
 int refresh_tile_count(PsimStepper* s) {
     if (s->nranks > 1 || !s->float_grid || !s->has_scene || s->compact_mode) return PSIM_OK;
-    uint32_t c[2] = {0, 0};
-    CK(cudaMemcpy(c, s->d_couple_tiles, sizeof c, cudaMemcpyDeviceToHost));
+    const uint32_t c[2] = {s->h_counts[12], s->h_counts[13]};  // row_tiles_kernel's mirror; the caller has waited for the stream
     if (c[1]) return fail(s, PSIM_ECAPACITY, "internal: more couple tiles than the %u there is room for", s->tiles_c_cap);
     set_tile_count(s, c[0]);
     return PSIM_OK;
@@ -1549,8 +1564,9 @@ int psim_create(const PsimConfig* config, PsimStepper** out) {
     CKC(cudaMalloc(&st->mig_counters, 2 * sizeof(uint32_t)));
     CKC(cudaMalloc(&st->d_flags, sizeof(uint32_t)));
     CKC(cudaMalloc(&st->d_counts, 16 * sizeof(uint32_t)));
-    CKC(cudaMallocHost(&st->h_counts, 16 * sizeof(uint32_t)));
+    CKC(cudaHostAlloc(&st->h_counts, 16 * sizeof(uint32_t), cudaHostAllocMapped));
     std::memset(st->h_counts, 0, 16 * sizeof(uint32_t));
+    CKC(cudaHostGetDevicePointer(reinterpret_cast<void**>(&st->h_counts_dev), st->h_counts, 0));
     CKC(cudaMemset(st->cell_start, 0, sizeof(uint32_t) * ((size_t)g.cells + 1 + kPadCells)));
     CKC(cudaMemset(st->d_flags, 0, sizeof(uint32_t)));
 #undef CKC

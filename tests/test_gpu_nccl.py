@@ -35,7 +35,13 @@ def test_nccl_slabs_metadata_change_between_frames():
     run_workers(2, "push", port=29660, meta_change=True)
 
 
-def run_workers(world, halo, bounds=None, port=None, meta_change=False):
+@pytest.mark.parametrize("world", [2, 4])
+def test_rebalance_across_processes(world):
+    """slabs.rebalance_across_ranks: boundaries moved between frames of a running one-process-per-GPU decomposition."""
+    run_workers(world, "push", port=29670 + world, script="mp_rebalance_worker.py")
+
+
+def run_workers(world, halo, bounds=None, port=None, meta_change=False, script="mp_slab_worker.py"):
     if _gpus() < world:
         pytest.skip(f"needs {world} GPUs, this box has {_gpus()}")
     env = dict(os.environ, PSIM_EXPECT_HALO=halo)
@@ -47,7 +53,7 @@ def run_workers(world, halo, bounds=None, port=None, meta_change=False):
         env["PSIM_TEST_META_CHANGE"] = "1"
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}",
            "--master-addr", "127.0.0.1", "--master-port", str(port or 29600 + world + (10 if halo == "nccl" else 0)),
-           os.path.join(REPO, "tests", "mp_slab_worker.py"), "3"]
+           os.path.join(REPO, "tests", script), "3"]
     # own session: if a rank hangs, the whole process group is killed, never left spinning on the GPUs
     proc = subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, cwd=REPO, env=env,
                             start_new_session=True)
