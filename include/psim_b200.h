@@ -70,6 +70,12 @@ typedef struct PsimConfig {
                                   slab 0 has {0, 0, ..}, the last slab {.., rows, rows}), e.g. from
                                   psim_balance_rows. Every slab owns at least 2 rows; adjacent slabs must meet
                                   (checked by psim_group_create / psim_comm_init).                          */
+    uint32_t species_physics;  /* 0: every particle is stepped with metadata.particles[0], as the reference does
+                                  (kernel_bucket.cuh:52); `ty` is a label. 1 (an extension): a
+                                  pair uses the Mie parameters of its species pair -- particles[s] for two particles
+                                  of species s = min(ty, 1), the Lorentz-Berthelot mix (mean sigma, geometric-mean
+                                  epsilon, mean exponents) for an unlike pair -- and the wall term the particle's own.
+                                  Takes effect when the two entries differ; MatrixBuckets scenes on a single slab.  */
 } PsimConfig;
 
 /* Defaults: 64x64 cells (the reference grid), 65536 particles, reference schedule, device -1. */

@@ -169,6 +169,8 @@ class PortOracle:
             L.oracle_move.argtypes = [vp, vp, CGrid]
             L.oracle_step.restype = None
             L.oracle_step.argtypes = [vp, vp, vp, CGrid, ctypes.c_uint32]
+            L.oracle_step_species.restype = None
+            L.oracle_step_species.argtypes = [vp, vp, vp, CGrid, ctypes.c_uint32]
             L.oracle_forces.restype = None
             L.oracle_forces.argtypes = [vp, vp, CGrid, vp, vp, vp]
             L.oracle_run_frame.restype = ctypes.c_uint32
@@ -210,6 +212,13 @@ class PortOracle:
         dst = np.zeros_like(slots)
         m = self._meta(meta)
         self.L.oracle_step(self._p(slots), self._p(dst), self._p(m), self.grid, threads)
+        return dst
+
+    def step_species(self, slots: np.ndarray, meta: np.ndarray, threads: int = 1) -> np.ndarray:
+        """The per-species extension (oracle_step_species): not reference behaviour, the spec of PsimConfig.species_physics."""
+        dst = np.zeros_like(slots)
+        m = self._meta(meta)
+        self.L.oracle_step_species(self._p(slots), self._p(dst), self._p(m), self.grid, threads)
         return dst
 
     def forces(self, slots: np.ndarray, meta: np.ndarray) -> tuple[np.ndarray, np.ndarray, np.ndarray]:

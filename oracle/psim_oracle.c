@@ -177,8 +177,12 @@ uint64_t oracle_move(const Particle* src, Particle* dst, OracleGrid g) {
 /* ---- force + integrate -------------------------------------------------------------------- */
 
 /* kernel_bucket.cuh:40-94 for one slot; if `out_f` is given the force is reported instead of integrated */
+/* `species`: 0 = the reference (q[0] for every particle, kernel_bucket.cuh:52); 1 = the per-species EXTENSION
+ * (oracle_step_species): q[0], q[1], q[2] are the species pairs 00, 01 (mixed), 11; the wall term uses the particle's own. */
+static int species_of(int32_t ty) { return ty > 0 ? 1 : 0; }
+
 static void step_slot(const Particle* src, Particle* dst, const FrameMetadata* f, OracleGrid g, const MieF* q,
-                      uint64_t i, float* out_f) {
+                      uint64_t i, float* out_f, int species) {
     if (dst) dst[i].ty = src[i].ty;
     if (src[i].ty < 0) {
         if (out_f) out_f[0] = out_f[1] = out_f[2] = 0.f;
@@ -186,8 +190,9 @@ static void step_slot(const Particle* src, Particle* dst, const FrameMetadata* f
     }
     uint32_t bx = 1u << g.lx, by = 1u << g.ly;
     float fx, fy, wx, wy;
+    const int si = species ? species_of(src[i].ty) : 0;
     cursor_force(&src[i], f, &fx, &fy);
-    wall_force(q, &src[i], f, &wx, &wy);
+    wall_force(species ? &q[2 * si] : q, &src[i], f, &wx, &wy);
     fx += wx;
     fy += wy;
 
@@ -204,7 +209,7 @@ static void step_slot(const Particle* src, Particle* dst, const FrameMetadata* f
                 if (j == i || src[j].ty < 0) continue;
                 float rx, ry, px, py;
                 separation(&src[i], &src[j], f, &rx, &ry);
-                pair_force(q, rx, ry, &px, &py);
+                pair_force(species ? &q[si + species_of(src[j].ty)] : q, rx, ry, &px, &py);
                 fx += px;
                 fy += py;
                 if (out_f) {
@@ -219,7 +224,7 @@ static void step_slot(const Particle* src, Particle* dst, const FrameMetadata* f
         out_f[1] = fy;
         out_f[2] = max_pair;
     }
-    if (dst) integrate(q, &dst[i], &src[i], fx, fy, f);
+    if (dst) integrate(q, &dst[i], &src[i], fx, fy, f); /* one mass for every species (particle.cuh:51) */
 }
 
 typedef struct StepJob {
@@ -228,26 +233,41 @@ typedef struct StepJob {
     const FrameMetadata* f;
     OracleGrid g;
     uint64_t i0, i1;
+    int species;
 } StepJob;
+
+/* Lorentz-Berthelot mix of the two species (the extension's unlike pair): mean sigma, geometric-mean epsilon, mean exponents */
+static MiePotentialParams mie_mix(MiePotentialParams a, MiePotentialParams b) {
+    MiePotentialParams m;
+    m.sigma = (a.sigma + b.sigma) * 0.5f;
+    m.epsilon = sqrtf(a.epsilon * b.epsilon);
+    m.n = (a.n + b.n) * 0.5f;
+    m.m = (a.m + b.m) * 0.5f;
+    return m;
+}
 
 static void* step_job(void* arg) {
     StepJob* j = (StepJob*)arg;
-    MieF q = mie_of(j->f->particles[0]); /* only species 0 is ever used: kernel_bucket.cuh:52 */
-    for (uint64_t i = j->i0; i < j->i1; ++i) step_slot(j->src, j->dst, j->f, j->g, &q, i, NULL);
+    MieF q[3];
+    q[0] = mie_of(j->f->particles[0]); /* the reference only ever uses species 0: kernel_bucket.cuh:52 */
+    q[1] = mie_of(mie_mix(j->f->particles[0], j->f->particles[1]));
+    q[2] = mie_of(j->f->particles[1]);
+    for (uint64_t i = j->i0; i < j->i1; ++i) step_slot(j->src, j->dst, j->f, j->g, q, i, NULL, j->species);
     return NULL;
 }
 
-void oracle_step(const Particle* src, Particle* dst, const FrameMetadata* meta, OracleGrid g, uint32_t threads) {
+static void step_all(const Particle* src, Particle* dst, const FrameMetadata* meta, OracleGrid g, uint32_t threads,
+                     int species) {
     uint64_t n = oracle_slot_count(g);
     if (threads <= 1) {
-        StepJob j = {src, dst, meta, g, 0, n};
+        StepJob j = {src, dst, meta, g, 0, n, species};
         step_job(&j);
         return;
     }
     pthread_t* th = (pthread_t*)malloc(sizeof(pthread_t) * threads);
     StepJob* jobs = (StepJob*)malloc(sizeof(StepJob) * threads);
     for (uint32_t t = 0; t < threads; ++t) {
-        StepJob j = {src, dst, meta, g, n * t / threads, n * (t + 1) / threads};
+        StepJob j = {src, dst, meta, g, n * t / threads, n * (t + 1) / threads, species};
         jobs[t] = j;
         pthread_create(&th[t], NULL, step_job, &jobs[t]);
     }
@@ -256,13 +276,21 @@ void oracle_step(const Particle* src, Particle* dst, const FrameMetadata* meta, 
     free(jobs);
 }
 
+void oracle_step(const Particle* src, Particle* dst, const FrameMetadata* meta, OracleGrid g, uint32_t threads) {
+    step_all(src, dst, meta, g, threads, 0);
+}
+
+void oracle_step_species(const Particle* src, Particle* dst, const FrameMetadata* meta, OracleGrid g, uint32_t threads) {
+    step_all(src, dst, meta, g, threads, 1);
+}
+
 void oracle_forces(const Particle* src, const FrameMetadata* meta, OracleGrid g, float* fx, float* fy,
                    float* max_pair) {
     uint64_t n = oracle_slot_count(g);
     MieF q = mie_of(meta->particles[0]);
     for (uint64_t i = 0; i < n; ++i) {
         float out[3];
-        step_slot(src, NULL, meta, g, &q, i, out);
+        step_slot(src, NULL, meta, g, &q, i, out, 0);
         fx[i] = out[0];
         fy[i] = out[1];
         max_pair[i] = out[2];

@@ -47,6 +47,12 @@ uint64_t oracle_move(const Particle* src, Particle* dst, OracleGrid g);
  * every slot is independent). */
 void oracle_step(const Particle* src, Particle* dst, const FrameMetadata* meta, OracleGrid g, uint32_t threads);
 
+/* EXTENSION, not in the reference (which steps every particle with metadata.particles[0], kernel_bucket.cuh:52): the same
+ * step with per-species Mie parameters -- a pair uses particles[s] when both particles are of species s = min(ty, 1), the
+ * Lorentz-Berthelot mix (mean sigma, geometric-mean epsilon, mean exponents) when they differ; the wall term uses the
+ * particle's own. It is the specification PsimConfig.species_physics is tested against; nothing in the reference pins it. */
+void oracle_step_species(const Particle* src, Particle* dst, const FrameMetadata* meta, OracleGrid g, uint32_t threads);
+
 /* The net force on every slot before integration (same accumulation order as oracle_step), plus
  * the largest single pair-force magnitude seen by that slot; for tolerance definitions. */
 void oracle_forces(const Particle* src, const FrameMetadata* meta, OracleGrid g, float* fx, float* fy,

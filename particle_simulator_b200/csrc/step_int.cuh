@@ -298,6 +298,123 @@ __global__ void __launch_bounds__(kTile, 8) step_kernel(const StepArgs a) {
 }
 
 // ------------------------------------------------------------------------------------------------
+// Per-species Mie parameters (PsimConfig.species_physics). An EXTENSION: the metadata carries two
+// MiePotentialParams (particle.rs:114) but the reference steps every particle with species 0's (kernel_bucket.cuh:52).
+// Here a pair (i, j) uses the parameters of its species pair -- like pairs their own, unlike pairs the Lorentz-
+// Berthelot mix sigma = (s0 + s1) / 2, epsilon = sqrt(e0 e1), exponents (n0 + n1) / 2, (m0 + m1) / 2 -- and the wall
+// term the particle's own. species = min(ty, 1). One particle per thread on step_kernel's tiles, general exponents
+// (2^(-e log2 r^2): MUFU.LG2 + two MUFU.EX2 per pair); the neighbours' labels are read from the sorted `ty` array.
+// Checked against oracle_step_species (oracle/psim_oracle.c), the same extension of the CPU restatement.
+// ------------------------------------------------------------------------------------------------
+struct SpeciesTab {
+    float inv_c2;      // kx^2 / sigma^2
+    float em, en;      // m / 2 + 1, n / 2 + 1
+    float nm;          // n / m
+    float pair_scale;  // C eps m kx / sigma^2
+    float sigma, wall_scale, m;  // the wall term of a particle of this (like-pair) species
+};
+
+struct SpeciesArgs {
+    SpeciesTab tab[3];  // species pairs 00, 01, 11 (index = species_i + species_j)
+    const int32_t* __restrict__ ty;
+};
+
+__device__ __forceinline__ int species_of(int32_t ty) { return ty > 0 ? 1 : 0; }
+
+__device__ __forceinline__ float species_wall_term(float d, const SpeciesTab& t) {
+    const float inv_d = fast_rcp(d);
+    return t.wall_scale * fast_ex2(t.m * fast_lg2(t.sigma * inv_d)) * inv_d;
+}
+
+template <bool ANISO>
+__global__ void __launch_bounds__(kTile) step_kernel_species(const StepArgs a, const SpeciesArgs sp) {
+    __shared__ __align__(16) uint32_t s_cs[3][kCsCap];
+    __shared__ __align__(16) uint2 s_pos[3][kPosCap];
+    __shared__ __align__(8) uint64_t s_bar;
+
+    const uint32_t b = blockIdx.x;
+    const uint32_t i = a.own_lo + b * kTile + threadIdx.x;
+    const TileDesc t = a.tiles[b];
+    if (t.fits) {
+        if (threadIdx.x == 0) {
+            mbar_init(&s_bar, 1);
+            uint32_t bytes = 0;
+#pragma unroll
+            for (int d = 0; d < 3; ++d) bytes += t.cs_cnt[d] * 4u + t.p_cnt[d] * 8u;
+            mbar_arrive_expect_tx(&s_bar, bytes);
+#pragma unroll
+            for (int d = 0; d < 3; ++d) {
+                if (t.cs_cnt[d]) bulk_copy_g2s(s_cs[d], a.cell_start + t.cs_lo[d], t.cs_cnt[d] * 4u, &s_bar);
+                if (t.p_cnt[d]) bulk_copy_g2s(s_pos[d], a.pos_in + t.p_lo[d], t.p_cnt[d] * 8u, &s_bar);
+            }
+        }
+        __syncthreads();
+    }
+    const bool live = i < a.own_hi;
+    uint2 pi = make_uint2(0, 0);
+    float2 vi = make_float2(0.f, 0.f);
+    uint32_t cell = 0;
+    int si = 0;
+    if (live) {
+        pi = a.pos_in[i];
+        vi = a.vel[i];
+        cell = a.cell_id[i];
+        si = species_of(sp.ty[i]);
+    }
+    if (t.fits) mbar_wait(&s_bar, 0);
+    if (!live) return;
+    const Grid& g = a.g;
+    const uint32_t cx = cell & (g.bx - 1), cy = cell >> g.lx;
+    const uint32_t x0 = cx == 0 ? 0 : cx - 1, x1 = cx == g.bx - 1 ? cx : cx + 1;
+    float fx = 0.f, fy = 0.f;
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+        const int row = (int)cy + d - 1;
+        if (row < 0 || row >= (int)g.by) continue;
+        const uint32_t c0 = ((uint32_t)row << g.lx) + x0, c1 = ((uint32_t)row << g.lx) + x1;
+        const uint32_t* cs = t.fits ? s_cs[d] - t.cs_lo[d] : a.cell_start;
+        const uint32_t ws = cs[c0], we = cs[c1 + 1];
+        const uint2* pp = t.fits ? s_pos[d] - t.p_lo[d] : a.pos_in;
+        for (uint32_t j = ws; j < we; ++j) {
+            const uint2 pj = t.fits ? pp[j] : __ldcg(pp + j);
+            const SpeciesTab& tab = sp.tab[si + species_of(__ldg(sp.ty + j))];
+            const float x = __int2float_rn((int)(pj.x - pi.x));
+            float y = __int2float_rn((int)(pj.y - pi.y));
+            if (ANISO) y *= a.ph.yscale;
+            const float r2 = fmaxf((x * x + y * y) * tab.inv_c2, 1e-2f);  // j == i: x = y = 0 contributes an exact 0
+            const float l = fast_lg2(r2);
+            const float gq = tab.pair_scale * (fast_ex2(-tab.em * l) - tab.nm * fast_ex2(-tab.en * l));
+            fx = fmaf(gq, x, fx);
+            fy = fmaf(gq, y, fy);
+        }
+    }
+    // cursor (kernel_bucket.cuh:54-67) and the walls with the particle's own species (particle.cuh:125-144)
+    const Phys& ph = a.ph;
+    const SpeciesTab& own = sp.tab[2 * si];
+    float2 f = make_float2(fx, fy);
+    if (ph.cursor_on) {
+        const float inv32 = 1.f / 4294967296.f;
+        const float dx = ph.cursor_x - __uint2float_rn(pi.x) * inv32, dy = ph.cursor_y - __uint2float_rn(pi.y) * inv32;
+        const float sq = dx * dx + dy * dy;
+        if (sq < ph.cursor_r2) {
+            const float c = 8e-12f * fast_rcp(sq + 1.f);
+            f.x += dx > 0 ? -c : c;
+            f.y += dy > 0 ? -c : c;
+        }
+    }
+    const bool left = pi.x < 0xFFFFFFFFu / 2, low = pi.y < 0xFFFFFFFFu / 2;
+    const float wx = species_wall_term(__uint2float_rn(left ? pi.x : 0xFFFFFFFFu - pi.x) * ph.kx, own);
+    const float wy = species_wall_term(__uint2float_rn(low ? pi.y : 0xFFFFFFFFu - pi.y) * ph.ky, own);
+    f.x += left ? wx : -wx;
+    f.y += low ? wy : -wy;
+    uint2 po;
+    float2 vo;
+    integrate(pi, vi, f, ph, po, vo);
+    a.pos_out[i] = po;
+    a.vel[i] = vo;
+}
+
+// ------------------------------------------------------------------------------------------------
 // DataStructure::CompactArray (kernel_compact.cuh:4-34): every particle interacts with every other one, particles
 // keep their input order, there is no grid. O(N^2): the reference's teaching baseline, offered so that the
 // metadata's data_structure switch (kernel.cuh:143-150) means here what it means there. One thread per particle;

@@ -144,6 +144,8 @@ struct PsimStepper {
     bool float_path = false;         // ... and the metadata's physics has a step_kernel_c variant
     PhysF physf{};
     bool force_int_path = false;     // PSIM_FORCE_INT_PATH=1: step_kernel on every grid (A/B measurements, tests)
+    bool species_mode = false;       // PsimConfig.species_physics and the metadata's two species differ: step_kernel_species
+    SpeciesArgs species{};
     uint32_t* cell_count = nullptr;  // cells
     uint2* block_sum = nullptr;      // per scan block: (particles, particles with every cell rounded up to even)
     uint32_t* rank_in_cell = nullptr;
@@ -427,12 +429,39 @@ bool make_phys_f(const FrameMetadata& m, const Phys& ph, const Grid& g, int kn, 
     return true;
 }
 
+// Pair tables of step_kernel_species: like pairs use their own parameters, the unlike pair the Lorentz-Berthelot mix.
+void make_species_tables(const FrameMetadata& m, const Phys& ph, SpeciesTab tab[3]) {
+    const MiePotentialParams& a = m.particles[0];
+    const MiePotentialParams& b = m.particles[1];
+    MiePotentialParams mix;
+    mix.sigma = (a.sigma + b.sigma) * 0.5f;
+    mix.epsilon = std::sqrt(a.epsilon * b.epsilon);
+    mix.n = (a.n + b.n) * 0.5f;
+    mix.m = (a.m + b.m) * 0.5f;
+    const MiePotentialParams pairs[3] = {a, mix, b};
+    for (int k = 0; k < 3; ++k) {
+        const MiePotentialParams& p = pairs[k];
+        const float C = (p.n / (p.n - p.m)) * powf(p.n / p.m, p.m / (p.n - p.m));  // particle.cuh:53-55
+        SpeciesTab& t = tab[k];
+        t.inv_c2 = (ph.kx / p.sigma) * (ph.kx / p.sigma);
+        t.em = p.m / 2.f + 1.f;
+        t.en = p.n / 2.f + 1.f;
+        t.nm = p.n / p.m;
+        t.pair_scale = C * p.epsilon * p.m * ph.kx / (p.sigma * p.sigma);
+        t.sigma = p.sigma;
+        t.wall_scale = C * p.epsilon * p.m;
+        t.m = p.m;
+    }
+}
+
 void apply_metadata(PsimStepper* s, const FrameMetadata& m) {
     // the same metadata again (a scene re-uploaded every frame by a pipelined host): captured frames stay valid
     const bool same = s->has_scene && std::memcmp(&s->meta, &m, sizeof m) == 0;
     s->meta = m;
     s->phys = make_phys(m, &s->kernel_kn, &s->kernel_frac, &s->kernel_aniso);
-    s->float_path = s->float_grid && !s->force_int_path &&
+    s->species_mode = s->cfg.species_physics && std::memcmp(&m.particles[0], &m.particles[1], sizeof(MiePotentialParams)) != 0;
+    if (s->species_mode) make_species_tables(m, s->phys, s->species.tab);
+    s->float_path = s->float_grid && !s->force_int_path && !s->species_mode &&
                     make_phys_f(m, s->phys, s->grid, s->kernel_kn, s->kernel_frac, &s->physf);
     s->nbr_stale = true;  // the records carry the old scale (or were not kept at all): rebuilt before the next step
     if (!same) drop_frame_graphs(s);  // captured launches carry the old constants
@@ -486,6 +515,12 @@ void launch_allpairs(PsimStepper* s, const StepArgs& a, uint32_t tiles) {
 void launch_step(PsimStepper* s, const StepArgs& a, uint32_t tiles) {
     if (s->compact_mode) {
         launch_allpairs(s, a, tiles);
+        return;
+    }
+    if (s->species_mode) {
+        s->species.ty = s->ty[s->cur_ty];
+        if (s->kernel_aniso) step_kernel_species<true><<<tiles, kTile, 0, s->stream>>>(a, s->species);
+        else step_kernel_species<false><<<tiles, kTile, 0, s->stream>>>(a, s->species);
         return;
     }
     if (s->float_path) {
@@ -1416,6 +1451,8 @@ int psim_create(const PsimConfig* config, PsimStepper** out) {
     if (config->max_particles == 0 || config->max_particles > 0x7FFFFF00u)
         return fail(s, PSIM_EINVAL, "psim_create: max_particles out of range");
     if (config->schedule > PSIM_SCHEDULE_NATIVE) return fail(s, PSIM_EINVAL, "psim_create: unknown schedule");
+    if (config->species_physics && config->slab_count > 1)
+        return fail(s, PSIM_EINVAL, "psim_create: species_physics is not available with slabs (ghost rows carry positions only)");
     const uint32_t nranks = config->slab_count ? config->slab_count : 1;
     const uint32_t rows_global = 1u << config->grid_y_log2;
     if (config->slab_rank >= nranks) return fail(s, PSIM_EINVAL, "psim_create: slab_rank %u of %u", config->slab_rank, nranks);

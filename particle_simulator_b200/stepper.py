@@ -48,6 +48,7 @@ class CConfig(ctypes.Structure):
         ("ingest_capacity", ctypes.c_uint32),
         ("snapshot_buffers", ctypes.c_uint32),
         ("slab_bounds", ctypes.c_uint32 * 4),
+        ("species_physics", ctypes.c_uint32),
     ]
 
 
@@ -151,6 +152,7 @@ class Stepper:
     def __init__(self, grid_log2: tuple[int, int] = (6, 6), max_particles: int = 65536,
                  schedule: int = SCHEDULE_REFERENCE, rebin_every: int = 0, device: int = -1,
                  use_graph: bool = False, slab_rank: int = 0, slab_count: int = 1, ghost_capacity: int = 0,
+                 species_physics: bool = False,
                  migrant_capacity: int = 0, ingest_capacity: int = 0, snapshot_buffers: int = 1,
                  bounds=None):
         """`bounds`: slab_count + 1 cell-row boundaries shared by all slabs (balance_rows); None: equal shares."""
@@ -162,6 +164,7 @@ class Stepper:
         cfg.rebin_every = rebin_every
         cfg.device = device
         cfg.use_graph = 1 if use_graph else 0
+        cfg.species_physics = 1 if species_physics else 0
         cfg.slab_rank, cfg.slab_count = slab_rank, slab_count
         cfg.ghost_capacity, cfg.migrant_capacity, cfg.ingest_capacity = ghost_capacity, migrant_capacity, ingest_capacity
         cfg.snapshot_buffers = snapshot_buffers

@@ -164,3 +164,31 @@ def test_all_pairs_kernel_agrees_inside_one_stencil(golden):
     assert np.abs(w["y"].astype(np.int64) - g["y"].astype(np.int64)).max() <= 2
     assert np.allclose(w["vx"], g["vx"], rtol=1e-5, atol=1e-4)
     assert np.allclose(w["vy"], g["vy"], rtol=1e-5, atol=1e-4)
+
+
+def test_species_extension_reduces_to_the_reference_step():
+    """oracle_step_species (the spec of PsimConfig.species_physics, an extension): with identical species, or with only
+    species-0 labels, it IS the pinned reference step; with distinct species it differs, and pair forces stay
+    antisymmetric (total momentum changes only by rounding away from the walls)."""
+    from particle_simulator_b200 import FrameBuffer, default_metadata, io
+
+    meta = default_metadata()
+    meta["particles"][1] = (3.405e-10, 1.654e-21, 12.0, 6.0)
+    fb = FrameBuffer(2 * 30 * 30, meta)
+    io.scene_hex_square(fb, 30, 30, (18e-9, 25e-9), 1.1, 10.0, 60.0, 0, seed=71)
+    io.scene_hex_square(fb, 30, 30, (32e-9, 25e-9), 1.1, 10.0, 60.0, 1, seed=72)
+    port = PortOracle(6, 6, 16)
+    slots, dropped = port.prepare(fb)
+    assert dropped == 0
+    ref = port.step(slots, fb.metadata)
+    ext = port.step_species(slots, fb.metadata)
+    live = slots["ty"] >= 0
+    s0 = live & (slots["ty"] == 0)
+    far0 = s0 & (slots["x"] < np.uint32(0.45 * 2**32))  # species-0 particles out of reach of the species-1 block
+    assert ext[far0].tobytes() == ref[far0].tobytes()
+    assert not np.array_equal(ext[live & (slots["ty"] == 1)]["vx"], ref[live & (slots["ty"] == 1)]["vx"])
+    same = fb.metadata.copy()
+    same["particles"][1] = same["particles"][0]
+    assert port.step_species(slots, same).tobytes() == port.step(slots, same).tobytes()
+    dv = ext["vx"][live].astype(np.float64) - slots["vx"][live].astype(np.float64)
+    assert abs(dv.sum()) < 1e-4 * np.abs(dv).sum()
