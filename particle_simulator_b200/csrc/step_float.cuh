@@ -310,40 +310,44 @@ __device__ __forceinline__ uint32_t cut_run(const uint32_t* __restrict__ cell_st
 
 // EMIT = false: tile_base[r] = number of tiles of owned row r (row_tiles_kernel turns the counts into bases in place).
 // EMIT = true: tiles[tile_base[r] ..] get their k0 / nk.
+// One WARP per row: the lanes fetch the couple index at every block boundary at once (a row of 2048 columns has 33 of them;
+// read one after the other by a single thread they were 33 dependent trips to L2), then lane 0 walks the blocks.
+constexpr int kCutRowsPerCta = 4;
+constexpr int kCutMaxBlocks = 32768 / kTileCols;  // grid_x_log2 <= 15
+
 template <bool EMIT>
-__global__ void row_cut_kernel(const uint32_t* __restrict__ cell_start, const uint32_t* __restrict__ pad_start, Grid g,
-                               uint32_t* __restrict__ tile_base, TileC* __restrict__ tiles, uint32_t tiles_cap) {
-    const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+__global__ void __launch_bounds__(32 * kCutRowsPerCta) row_cut_kernel(const uint32_t* __restrict__ cell_start,
+                                                                      const uint32_t* __restrict__ pad_start, Grid g,
+                                                                      uint32_t* __restrict__ tile_base, TileC* __restrict__ tiles,
+                                                                      uint32_t tiles_cap) {
+    __shared__ uint32_t s_kb[kCutRowsPerCta][kCutMaxBlocks + 1];  // first couple of every block of the row, and the row's end
+    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
+    const uint32_t r = blockIdx.x * kCutRowsPerCta + warp;
     if (r >= g.own_rows) return;
     const uint32_t c0 = (g.own_row0 + r) << g.lx;
     const uint32_t nb = g.bx / kTileCols;
+    uint32_t* kb = s_kb[warp];
+    for (uint32_t b = lane; b <= nb; b += 32) kb[b] = pad_start[c0 + b * kTileCols] >> 1;
+    __syncwarp();
+    if (lane != 0) return;
     const uint32_t base = EMIT ? tile_base[r] : 0u;
-    uint32_t k_at = pad_start[c0] >> 1;  // first couple of block b
-    uint32_t k_end = pad_start[c0 + kTileCols] >> 1;
-    uint32_t cnt_prev = 0, cnt_cur = k_end - k_at;
-    uint32_t run_k0 = k_at, run_b0 = 0, n = 0;
+    uint32_t cnt_prev = 0, cnt_cur = kb[1] - kb[0];
+    uint32_t run_b0 = 0, n = 0;
     bool run_dense = false;
     for (uint32_t b = 0; b < nb; ++b) {
-        uint32_t cnt_next = 0;
-        if (b + 1 < nb) {
-            const uint32_t k_next_end = pad_start[c0 + (b + 2) * kTileCols] >> 1;
-            cnt_next = k_next_end - k_end;
-            k_end = k_next_end;
-        }
+        const uint32_t cnt_next = b + 1 < nb ? kb[b + 2] - kb[b + 1] : 0u;
         const bool dense = cnt_cur >= kSparseCouples || (cnt_cur > 0 && (cnt_prev >= kSparseCouples || cnt_next >= kSparseCouples));
         if (b == 0) {
             run_dense = dense;
         } else if (dense != run_dense) {
-            n += cut_run<EMIT>(cell_start, g, g.own_row0 + r, run_b0, b, run_k0, k_at, run_dense, base + n, tiles, tiles_cap);
-            run_k0 = k_at;
+            n += cut_run<EMIT>(cell_start, g, g.own_row0 + r, run_b0, b, kb[run_b0], kb[b], run_dense, base + n, tiles, tiles_cap);
             run_b0 = b;
             run_dense = dense;
         }
-        k_at += cnt_cur;
         cnt_prev = cnt_cur;
         cnt_cur = cnt_next;
     }
-    n += cut_run<EMIT>(cell_start, g, g.own_row0 + r, run_b0, nb, run_k0, k_at, run_dense, base + n, tiles, tiles_cap);
+    n += cut_run<EMIT>(cell_start, g, g.own_row0 + r, run_b0, nb, kb[run_b0], kb[nb], run_dense, base + n, tiles, tiles_cap);
     if (!EMIT) tile_base[r] = n;
 }
 

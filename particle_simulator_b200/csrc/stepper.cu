@@ -701,7 +701,7 @@ int enqueue_scan(PsimStepper* s) {
     s->launches += 3;
     if (s->float_grid) {
         couple_build_kernel<<<div_up(cells, 256), 256, 0, s->stream>>>(s->cell_start, s->pad_start, cells, s->couple_i0);
-        row_cut_kernel<false><<<div_up(s->grid.own_rows, 64), 64, 0, s->stream>>>(s->cell_start, s->pad_start, s->grid,
+        row_cut_kernel<false><<<div_up(s->grid.own_rows, kCutRowsPerCta), 32 * kCutRowsPerCta, 0, s->stream>>>(s->cell_start, s->pad_start, s->grid,
                                                                                 s->tile_base, s->tiles_c, s->tiles_c_cap);
         row_tiles_kernel<<<1, 1024, 0, s->stream>>>(s->grid, s->tile_base, s->tiles_c_cap, s->d_couple_tiles,
                                                     s->h_counts_dev + 12);
@@ -890,7 +890,7 @@ int bin_phase_tiles(PsimStepper* s) {
         if (rc) return rc;
     }
     if (s->float_grid) {
-        row_cut_kernel<true><<<div_up(s->grid.own_rows, 64), 64, 0, s->stream>>>(s->cell_start, s->pad_start, s->grid,
+        row_cut_kernel<true><<<div_up(s->grid.own_rows, kCutRowsPerCta), 32 * kCutRowsPerCta, 0, s->stream>>>(s->cell_start, s->pad_start, s->grid,
                                                                                s->tile_base, s->tiles_c, s->tiles_c_cap);
         s->launches += 1;
         // with slabs the host knows the count of this binning; a single slab covers whatever the count has become

@@ -24,15 +24,38 @@ def pinned(n):
 
 
 keep = []
-t, a = pinned(3162 * 3163)
-keep.append(t)
-wl = workloads.config_10m_solid(storage=a)
+rank, world, local = (int(os.environ.get(k, d)) for k, d in (("RANK", 0), ("WORLD_SIZE", 1), ("LOCAL_RANK", 0)))
+torch.cuda.set_device(local)
+if world > 1:  # one slab per rank (torchrun), the weak-scaling workload of bench.py
+    import torch.distributed as dist
+
+    from particle_simulator_b200 import slabs
+
+    dev = torch.device("cuda", local)
+    dist.init_process_group("nccl", device_id=dev)
+
+    def storage(count):
+        t, a = pinned(count)
+        keep.append(t)
+        return a
+
+    wl = workloads.slab_crystal(rank, world, storage_factory=storage)
+    cap = int(1.05 * 3162 * 3163)
+    uid = slabs.broadcast_bytes(dist, Stepper.comm_unique_id() if rank == 0 else None, 128, device=dev)
+    st = Stepper(wl.grid_log2, cap, device=local, slab_rank=rank, slab_count=world, ingest_capacity=wl.frame.count,
+                 snapshot_buffers=2)
+    st.comm_init(uid)
+else:
+    t, a = pinned(3162 * 3163)
+    keep.append(t)
+    wl = workloads.config_10m_solid(storage=a)
+    cap = wl.particles
+    st = Stepper(wl.grid_log2, wl.particles, device=local, snapshot_buffers=2, use_graph=use_graph)
 wl.frame.metadata["steps_per_frame"] = 100
-t, a = pinned(wl.particles)
+t, a = pinned(cap)
 keep.append(t)
-out = FrameBuffer(wl.particles, storage=a)
+out = FrameBuffer(cap, storage=a)
 stream = torch.cuda.Stream()
-st = Stepper(wl.grid_log2, wl.particles, device=0, snapshot_buffers=2, use_graph=use_graph)
 st.set_stream(stream.cuda_stream)
 names = ["ev0", "upload_staged", "ev1", "stage_async", "run_frame_async", "ev2", "download_end", "download_begin"]
 steps = 6
@@ -65,8 +88,13 @@ for rep in range(3):
     ingest = sum(ev[k][0].elapsed_time(ev[k][1]) for k in range(1, steps)) / (steps - 1)
     frame = sum(ev[k][1].elapsed_time(ev[k][2]) for k in range(1, steps)) / (steps - 1)
     period = ev[1][0].elapsed_time(ev[steps - 1][0]) / (steps - 2)
-    print(f"rep {rep} ({'graph' if use_graph else 'launch by launch'}): {1e3 * tot / steps:.2f} ms/step; host: "
+    if world > 1:
+        dist.barrier()
+    if rank == 0:
+      print(f"rep {rep} ({'graph' if use_graph else 'launch by launch'}): {1e3 * tot / steps:.2f} ms/step; host: "
           + ", ".join(f"{n} {1e3 * v / steps:.2f}" for n, v in acc.items())
           + f"; device: ingest {ingest:.2f} ms (event to event, incl. any wait for the staged copy), frame + snapshot {frame:.2f} ms, "
-            f"period {period:.2f} ms")
+            f"period {period:.2f} ms", flush=True)
 st.close()
+if world > 1:
+    dist.destroy_process_group()
