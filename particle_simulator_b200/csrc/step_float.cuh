@@ -33,7 +33,10 @@
 
 constexpr int kColCap = 128;   // cell columns a tile's stencil rows may span (its own columns +- 1)
 constexpr int kCsRow = 136;    // cell_start entries staged per row: kColCap + 1, + 3 alignment slack, multiple of 4
-constexpr int kRowCap = 448;   // neighbour records staged per stencil row (a crystal at r0 has rows of 6 per cell)
+#ifndef PSIM_ROW_CAP
+#define PSIM_ROW_CAP 448
+#endif
+constexpr int kRowCap = PSIM_ROW_CAP;   // neighbour records staged per stencil row (a crystal at r0 has rows of 6 per cell)
 constexpr int kCouples = 128;  // couples (= threads) per tile
 #ifndef PSIM_MIN_CTAS
 #define PSIM_MIN_CTAS 9  // CTAs per SM the register allocation aims at (56 registers per thread)
@@ -267,7 +270,7 @@ __global__ void couple_build_kernel(const uint32_t* __restrict__ cell_start, con
 // A row that is dense from its first particle to its last (a crystal, a liquid) is one run.
 constexpr int kTileCols = 64;             // block width of the dense / sparse classification
 constexpr int kTileColsMax = kColCap - 2; // occupied columns a staged tile may span (its stencil rows: +- 1 column)
-constexpr uint32_t kRowFill = 384;        // staged particles per stencil row a cut aims at (kRowCap with slack for uneven rows)
+constexpr uint32_t kRowFill = kRowCap - 64;  // staged particles per stencil row a cut aims at (kRowCap with slack for uneven rows)
 constexpr uint32_t kSparseCouples = 32;
 
 template <bool EMIT>
