@@ -270,7 +270,10 @@ __global__ void couple_build_kernel(const uint32_t* __restrict__ cell_start, con
 // A row that is dense from its first particle to its last (a crystal, a liquid) is one run.
 constexpr int kTileCols = 64;             // block width of the dense / sparse classification
 constexpr int kTileColsMax = kColCap - 2; // occupied columns a staged tile may span (its stencil rows: +- 1 column)
-constexpr uint32_t kRowFill = kRowCap - 64;  // staged particles per stencil row a cut aims at (kRowCap with slack for uneven rows)
+#ifndef PSIM_ROW_FILL
+#define PSIM_ROW_FILL (PSIM_ROW_CAP - 64)
+#endif
+constexpr uint32_t kRowFill = PSIM_ROW_FILL;  // staged particles per stencil row a cut aims at (kRowCap with slack for uneven rows)
 constexpr uint32_t kSparseCouples = 32;
 
 template <bool EMIT>

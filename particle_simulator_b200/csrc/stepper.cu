@@ -201,6 +201,7 @@ struct PsimStepper {
     std::map<uint32_t, FrameGraph> frame_graphs;  // PsimConfig.use_graph: captured frames by starting buffer parity
 
     bool timing = false;
+    cudaEvent_t timing_after_main = nullptr;  // to be recorded right behind the step kernel of the launch in flight
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> timing_events;
     size_t timing_used = 0;
     double timing_total_ms = 0;
@@ -490,6 +491,10 @@ void launch_step_c(PsimStepper* s, const StepArgs& a) {
     ac.n_tiles = s->d_couple_tiles;
     if (s->kernel_frac == kFracNone) step_kernel_c<KN, kFracNone><<<s->tiles_c_launch, kCouples, 0, s->stream>>>(a, ac);
     else step_kernel_c<KN, kFracPoly><<<s->tiles_c_launch, kCouples, 0, s->stream>>>(a, ac);
+    if (s->timing_after_main) {  // step timing brackets the step kernel itself, not its tail launch
+        cudaEventRecord(s->timing_after_main, s->stream);
+        s->timing_after_main = nullptr;
+    }
     if (s->nranks > 1) return;  // slabs launch exactly the tiles there are
     // a single slab sized the launch from the count it last saw: whatever the last re-bin made beyond it
     if (s->kernel_frac == kFracNone)
@@ -799,6 +804,10 @@ void set_tile_count(PsimStepper* s, uint32_t count) {
     }
     uint32_t want = std::min(s->tiles_c_cap, count + count / 64 + 32);
     bool keep = s->tiles_c_launch >= std::min(s->tiles_c_cap, count + count / 256 + 8) && s->tiles_c_launch <= want + want / 16;
+    if (getenv("PSIM_TILE_EXACT")) {  // measurements: no margin
+        want = count;
+        keep = false;
+    }
     if (const char* env = getenv("PSIM_TILE_LAUNCH_CAP")) {  // tests: fewer CTAs than tiles, the surplus loop steps the rest
         want = std::max(1u, std::min(want, (uint32_t)std::atoi(env)));
         keep = false;
@@ -1053,8 +1062,12 @@ int enqueue_step(PsimStepper* s) {
         s->timing_used += 1;
         CK(cudaEventRecord(e0, s->stream));
     }
+    s->timing_after_main = s->timing ? e1 : nullptr;
     launch_step(s, a, tiles);
-    if (s->timing) CK(cudaEventRecord(e1, s->stream));
+    if (s->timing_after_main) {
+        CK(cudaEventRecord(e1, s->stream));
+        s->timing_after_main = nullptr;
+    }
     CK(cudaGetLastError());
     s->launches += 1;
     s->cur_pos ^= 1;
