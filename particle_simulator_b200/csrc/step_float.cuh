@@ -41,6 +41,12 @@ constexpr int kCouples = 128;  // couples (= threads) per tile
 #ifndef PSIM_MIN_CTAS
 #define PSIM_MIN_CTAS 9  // CTAs per SM the register allocation aims at (56 registers per thread)
 #endif
+#ifndef PSIM_LATE_LOADS
+#define PSIM_LATE_LOADS 1
+#endif
+#ifndef PSIM_OPAQUE_CONSTS
+#define PSIM_OPAQUE_CONSTS 1
+#endif
 #ifndef PSIM_PAIR_UNROLL
 #define PSIM_PAIR_UNROLL 1
 #endif
@@ -61,17 +67,18 @@ static_assert(sizeof(TileC) == 64, "TileC is read as four 16-byte words");
 struct StepArgsC {
     const uint2* __restrict__ couple_i0;  // per couple: (index of its first particle | (has a second one) << 31, its cell)
     const TileC* __restrict__ tiles;
-    // How many tiles the last binning made, in device memory: the host sizes the launch from the count it last saw
-    // plus a margin (it does not wait for a re-bin to learn the new one), CTAs beyond the count leave at once, and if
-    // the count ever outgrows the launch the first CTAs of the grid step the surplus tiles as well.
-    const uint32_t* __restrict__ n_tiles;
+    const uint32_t* __restrict__ n_tiles;  // tiles of the last binning, in device memory (read by the surplus launch only)
 };
 
 // One staged neighbour (its x offset of the thread's zone parity, its y) against the thread's two particles.
 // nx, ny: minus their own offsets.  g f^(2 km) = qs^4 - (n/m) f^(-2(kn-4)) qs^KN q^fn  with qs = 1 / (scaled r^2);
 // see make_phys_f().
+struct PolyC {  // the cubic's coefficients, held in registers across the pair loops (step_tile_c)
+    float d0, d1, d2, d3;
+};
+
 template <int KN, int FRAC, bool CLAMP>
-__device__ __forceinline__ void pairc(float xj, float yj, float2 nx, float2 ny, const PhysF& pf, float2& gx, float2& gy) {
+__device__ __forceinline__ void pairc(float xj, float yj, float2 nx, float2 ny, const PolyC& pf, float2& gx, float2& gy) {
     float2 x = __fadd2_rn(nx, splat(xj));
     float2 y = __fadd2_rn(ny, splat(yj));
     float2 r2 = __ffma2_rn(y, y, __fmul2_rn(x, x));
@@ -114,8 +121,9 @@ struct SmemC {
     uint64_t bar;
 };
 
-// One tile: stage its stencil, step its couples.
-template <int KN, int FRAC>
+// One tile: stage its stencil, step its couples. MAIN: called by step_kernel_c itself (whose first CTA publishes the
+// epoch of a boundary row without particles), not for a surplus tile.
+template <int KN, int FRAC, bool MAIN>
 __device__ __forceinline__ void step_tile_c(const StepArgs& a, const StepArgsC& ac, uint32_t tile, SmemC& sm) {
     float4 (&s_nb)[3][kRowCap] = sm.nb;
     uint32_t (&s_cs)[3][kCsRow] = sm.cs;
@@ -127,7 +135,10 @@ __device__ __forceinline__ void step_tile_c(const StepArgs& a, const StepArgsC& 
     const bool live = threadIdx.x < t.nk;
 
     if (a.push) {  // uniform over the grid
-        if (threadIdx.x == 0) halo_wait(a, tile);  // tiles next to a ghost row: the neighbour's last step has landed
+        if (threadIdx.x == 0) {
+            if (MAIN && blockIdx.x == 0) halo_publish_empty(a);
+            halo_wait(a, tile);  // tiles next to a ghost row: the neighbour's last step has landed
+        }
         if (!t.fits) __syncthreads();  // the global-memory path reads the ghost rows directly
     }
     if (!t.fits) {  // very sparse or very crowded spot: same physics straight from global memory, one particle at a time
@@ -175,9 +186,16 @@ __device__ __forceinline__ void step_tile_c(const StepArgs& a, const StepArgsC& 
         cell = w.y;
     }
     const uint32_t i1 = i0 + has1;  // a half-empty couple computes its only particle twice
+#if PSIM_LATE_LOADS
+    // positions and velocities are needed by the epilogue only: fetched into L1 now, read after the pair loops (eight
+    // registers that would otherwise stay live across the loops and push the cubic's constants out of the register file)
+    asm volatile("prefetch.global.L1 [%0];" ::"l"(a.pos_in + i0));
+    asm volatile("prefetch.global.L1 [%0];" ::"l"(a.vel + i0));
+#else
     // positions and velocities are needed by the epilogue only: these loads fly during the pair loops
     const uint2 p0 = a.pos_in[i0], p1 = a.pos_in[i1];
     const float2 v0 = a.vel[i0], v1 = a.vel[i1];
+#endif
     const uint32_t cx = cell & (g.bx - 1);
     const uint32_t x0c = cx == 0 ? 0 : cx - 1, x1c = cx == g.bx - 1 ? cx : cx + 1;
     const uint32_t par = (x0c >> pf.zl) & 1u;  // parity of the thread's zone: which x offset of a record it reads
@@ -192,6 +210,18 @@ __device__ __forceinline__ void step_tile_c(const StepArgs& a, const StepArgsC& 
     const float2 o0 = own[2 * (i0 - t.p_lo[1])], o1 = own[2 * (i1 - t.p_lo[1])];
     const float2 nx = make_float2(-o0.x, -o1.x), ny0 = make_float2(-o0.y, -o1.y);
 
+    // The cubic's four coefficients are read ONCE into registers through an opaque move: left to itself the compiler
+    // re-reads them from the constant bank in every trip of two of the three loops (two LDC.64 of 24 instructions).
+    PolyC pc;
+#if PSIM_OPAQUE_CONSTS
+    const float zero = __int_as_float(t.row & 0x80000000u);  // +0.0 (a row index has no bit 31), but only at run time
+    pc.d0 = pf.d0 + zero;
+    pc.d1 = pf.d1 + zero;
+    pc.d2 = pf.d2 + zero;
+    pc.d3 = pf.d3 + zero;
+#else
+    pc.d0 = pf.d0, pc.d1 = pf.d1, pc.d2 = pf.d2, pc.d3 = pf.d3;
+#endif
     float2 gx = splat(0.f), gy = splat(0.f);
 #pragma unroll
     for (int d = 0; d < 3; ++d) {
@@ -206,10 +236,14 @@ __device__ __forceinline__ void step_tile_c(const StepArgs& a, const StepArgsC& 
 #pragma unroll kPairUnroll
         for (; pj < pj_end; pj += 2) {
             const float2 j = *pj;
-            if (d == 1) pairc<KN, FRAC, true>(j.x, j.y, nx, ny, pf, gx, gy);
-            else pairc<KN, FRAC, false>(j.x, j.y, nx, ny, pf, gx, gy);
+            if (d == 1) pairc<KN, FRAC, true>(j.x, j.y, nx, ny, pc, gx, gy);
+            else pairc<KN, FRAC, false>(j.x, j.y, nx, ny, pc, gx, gy);
         }
     }
+#if PSIM_LATE_LOADS
+    const uint2 p0 = a.pos_in[i0], p1 = a.pos_in[i1];
+    const float2 v0 = a.vel[i0], v1 = a.vel[i1];
+#endif
     const RecOrigin org = rec_origin(cell, g, pf);  // both particles are members of the same cell
     finish_particle<true>(i0, p0, v0, cell, gx.x, gy.x, pf.pair_scale, pf.pair_scale, a, &org);  // KN > 0 implies m == 6
     if (has1) finish_particle<true>(i1, p1, v1, cell, gx.y, gy.y, pf.pair_scale, pf.pair_scale, a, &org);
@@ -217,17 +251,18 @@ __device__ __forceinline__ void step_tile_c(const StepArgs& a, const StepArgsC& 
 
 // The grid is the tile count the host last saw plus a margin (exactly the count when it has just read it: slabs). The
 // binning writes EMPTY descriptors (nk = 0) behind the last tile up to the size of the launch, so a surplus CTA leaves as
-// soon as it has read its descriptor and nobody waits for the count.
+// soon as it has read its descriptor and nobody waits for the count. The kernel steps exactly one tile and ends with the
+// tile body: any code BEHIND it -- a loop over more tiles, a call, even one never taken -- was measured at +2 to +4 %
+// (threads can no longer exit early, branches lose their reconvergence hints: tools/ab_step.py, profiles/r02_ab_step.txt).
 template <int KN, int FRAC>
 __global__ void __launch_bounds__(kCouples, PSIM_MIN_CTAS) step_kernel_c(const StepArgs a, const StepArgsC ac) {
     __shared__ __align__(16) SmemC sm;
-    if (a.push && blockIdx.x == 0 && threadIdx.x == 0) halo_publish_empty(a);
-    step_tile_c<KN, FRAC>(a, ac, halo_tile_order(a, blockIdx.x, gridDim.x), sm);
+    step_tile_c<KN, FRAC, true>(a, ac, halo_tile_order(a, blockIdx.x, gridDim.x), sm);
 }
 
 // Surplus TILES: the count grew past the launch, which the host's margin makes rare. A single slab follows every step
-// launch with this one (a few CTAs that read the count from device memory and, almost always, leave): tiles
-// [first, count) in turn. Kept out of step_kernel_c so that the kernel proper is compiled for exactly one tile.
+// launch with this one (a few CTAs that read the count from device memory and, almost always, leave at once: 2.6 us):
+// tiles [first, count) in turn.
 constexpr uint32_t kSurplusCtas = 128;
 
 template <int KN, int FRAC>
@@ -235,7 +270,7 @@ __global__ void __launch_bounds__(kCouples) step_kernel_c_surplus(const StepArgs
     __shared__ __align__(16) SmemC sm;
     const uint32_t count = *ac.n_tiles;
     for (uint32_t tile = first + blockIdx.x; tile < count; tile += gridDim.x) {
-        step_tile_c<KN, FRAC>(a, ac, tile, sm);
+        step_tile_c<KN, FRAC, false>(a, ac, tile, sm);
         __syncthreads();  // everybody has left the staging buffers and the barrier before the next tile re-arms them
         if (threadIdx.x == 0) asm volatile("mbarrier.inval.shared::cta.b64 [%0];" ::"r"(smem_u32(&sm.bar)) : "memory");
         __syncthreads();
@@ -269,7 +304,10 @@ __global__ void couple_build_kernel(const uint32_t* __restrict__ cell_start, con
 // the staging buffers and they run from global memory.
 // A row that is dense from its first particle to its last (a crystal, a liquid) is one run.
 constexpr int kTileCols = 64;             // block width of the dense / sparse classification
-constexpr int kTileColsMax = kColCap - 2; // occupied columns a staged tile may span (its stencil rows: +- 1 column)
+#ifndef PSIM_TILE_COLS_MAX
+#define PSIM_TILE_COLS_MAX (kColCap - 2)
+#endif
+constexpr int kTileColsMax = PSIM_TILE_COLS_MAX; // occupied columns a staged tile may span (its stencil rows: +- 1 column)
 #ifndef PSIM_ROW_FILL
 #define PSIM_ROW_FILL (PSIM_ROW_CAP - 64)
 #endif
@@ -404,11 +442,12 @@ __global__ void __launch_bounds__(1024) row_tiles_kernel(Grid g, uint32_t* __res
 // One TileC per tile index b in [0, n_tiles[0]); row_cut_kernel<true> has written its k0 / nk.
 __global__ void tile_build_kernel(const uint32_t* __restrict__ cell_start, const uint32_t* __restrict__ pad_start,
                                   const uint32_t* __restrict__ tile_base, const uint32_t* __restrict__ n_tiles,
-                                  uint32_t clear_upto, const uint2* __restrict__ couple_i0, Grid g,
+                                  uint32_t launch, const uint2* __restrict__ couple_i0, Grid g,
                                   TileC* __restrict__ tiles) {
     const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
-    if (b >= n_tiles[0]) {  // behind the last tile, as far as a step launches CTAs: empty descriptors
-        if (b < clear_upto) {
+    const uint32_t count = n_tiles[0];
+    if (b >= count) {  // behind the last tile, as far as a step launches CTAs: empty descriptors
+        if (b < launch) {
             TileC t;
             t.k0 = t.nk = t.row = t.fits = 0;
             for (int d = 0; d < 3; ++d) t.cs_lo[d] = t.cs_cnt[d] = t.p_lo[d] = t.p_cnt[d] = 0;
@@ -419,18 +458,19 @@ __global__ void tile_build_kernel(const uint32_t* __restrict__ cell_start, const
     // the last row whose base is <= b (rows without tiles share their successor's base and are skipped over)
     const uint32_t r = (uint32_t)last_le(tile_base, (int)g.own_rows, b);
     const uint32_t row = g.own_row0 + r;
+    const uint32_t nk = tiles[b].nk;  // as row_cut_kernel<true> left it: <= kCouples
     TileC t;
     t.k0 = tiles[b].k0;
-    t.nk = tiles[b].nk;
+    t.nk = nk;
     t.row = row;
-    if (t.nk == 0) {  // nothing to step: no staging either
+    if (nk == 0) {  // nothing to step: no staging either
         t.fits = 0;
         for (int d = 0; d < 3; ++d) t.cs_lo[d] = t.cs_cnt[d] = t.p_lo[d] = t.p_cnt[d] = 0;
         tiles[b] = t;
         return;
     }
     const uint32_t c_first = couple_i0[t.k0].y & (g.bx - 1);
-    const uint32_t c_last = couple_i0[t.k0 + t.nk - 1].y & (g.bx - 1);
+    const uint32_t c_last = couple_i0[t.k0 + nk - 1].y & (g.bx - 1);
     const uint32_t col_lo = c_first == 0 ? 0 : c_first - 1;
     const uint32_t col_hi = c_last == g.bx - 1 ? c_last : c_last + 1;
     bool fits = col_hi - col_lo + 1 <= (uint32_t)kColCap;
@@ -452,3 +492,4 @@ __global__ void tile_build_kernel(const uint32_t* __restrict__ cell_start, const
     t.fits = fits ? bytes : 0u;
     tiles[b] = t;
 }
+

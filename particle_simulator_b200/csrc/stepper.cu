@@ -808,7 +808,7 @@ void set_tile_count(PsimStepper* s, uint32_t count) {
         want = count;
         keep = false;
     }
-    if (const char* env = getenv("PSIM_TILE_LAUNCH_CAP")) {  // tests: fewer CTAs than tiles, the surplus loop steps the rest
+    if (const char* env = getenv("PSIM_TILE_LAUNCH_CAP")) {  // tests: fewer CTAs than tiles, the surplus launch steps the rest
         want = std::max(1u, std::min(want, (uint32_t)std::atoi(env)));
         keep = false;
     }
