@@ -257,6 +257,7 @@ __device__ __forceinline__ void step_tile_c(const StepArgs& a, const StepArgsC& 
 template <int KN, int FRAC>
 __global__ void __launch_bounds__(kCouples, PSIM_MIN_CTAS) step_kernel_c(const StepArgs a, const StepArgsC ac) {
     __shared__ __align__(16) SmemC sm;
+    asm volatile("griddepcontrol.wait;" ::: "memory");  // a no-op unless the launch allowed programmatic dependent launch
     step_tile_c<KN, FRAC, true>(a, ac, halo_tile_order(a, blockIdx.x, gridDim.x), sm);
 }
 
@@ -268,6 +269,7 @@ constexpr uint32_t kSurplusCtas = 128;
 template <int KN, int FRAC>
 __global__ void __launch_bounds__(kCouples) step_kernel_c_surplus(const StepArgs a, const StepArgsC ac, uint32_t first) {
     __shared__ __align__(16) SmemC sm;
+    asm volatile("griddepcontrol.wait;" ::: "memory");
     const uint32_t count = *ac.n_tiles;
     for (uint32_t tile = first + blockIdx.x; tile < count; tile += gridDim.x) {
         step_tile_c<KN, FRAC, false>(a, ac, tile, sm);

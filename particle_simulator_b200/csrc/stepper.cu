@@ -144,6 +144,7 @@ struct PsimStepper {
     bool float_path = false;         // ... and the metadata's physics has a step_kernel_c variant
     PhysF physf{};
     bool force_int_path = false;     // PSIM_FORCE_INT_PATH=1: step_kernel on every grid (A/B measurements, tests)
+    bool pdl = true;                 // step launches allow programmatic dependent launch (PSIM_PDL=0 turns it off)
     bool species_mode = false;       // PsimConfig.species_physics and the metadata's two species differ: step_kernel_species
     SpeciesArgs species{};
     uint32_t* cell_count = nullptr;  // cells
@@ -483,14 +484,30 @@ void launch_step_frac(PsimStepper* s, const StepArgs& a, uint32_t tiles) {
     }
 }
 
+// Launch with programmatic dependent launch allowed (the kernel starts with griddepcontrol.wait): its CTAs may be placed
+// while the previous kernel of the stream drains, so the launch latency hides behind that kernel's last wave.
+template <typename... Params, typename... Args>
+void launch_pdl(PsimStepper* s, void (*kernel)(Params...), uint32_t grid, uint32_t block, Args... args) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(block);
+    cfg.stream = s->stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = s->pdl ? 1 : 0;
+    cudaLaunchKernelEx(&cfg, kernel, args...);
+}
+
 template <int KN>
 void launch_step_c(PsimStepper* s, const StepArgs& a) {
     StepArgsC ac;
     ac.couple_i0 = s->couple_i0;
     ac.tiles = s->tiles_c;
     ac.n_tiles = s->d_couple_tiles;
-    if (s->kernel_frac == kFracNone) step_kernel_c<KN, kFracNone><<<s->tiles_c_launch, kCouples, 0, s->stream>>>(a, ac);
-    else step_kernel_c<KN, kFracPoly><<<s->tiles_c_launch, kCouples, 0, s->stream>>>(a, ac);
+    if (s->kernel_frac == kFracNone) launch_pdl(s, step_kernel_c<KN, kFracNone>, s->tiles_c_launch, kCouples, a, ac);
+    else launch_pdl(s, step_kernel_c<KN, kFracPoly>, s->tiles_c_launch, kCouples, a, ac);
     if (s->timing_after_main) {  // step timing brackets the step kernel itself, not its tail launch
         cudaEventRecord(s->timing_after_main, s->stream);
         s->timing_after_main = nullptr;
@@ -498,9 +515,9 @@ void launch_step_c(PsimStepper* s, const StepArgs& a) {
     if (s->nranks > 1) return;  // slabs launch exactly the tiles there are
     // a single slab sized the launch from the count it last saw: whatever the last re-bin made beyond it
     if (s->kernel_frac == kFracNone)
-        step_kernel_c_surplus<KN, kFracNone><<<kSurplusCtas, kCouples, 0, s->stream>>>(a, ac, s->tiles_c_launch);
+        launch_pdl(s, step_kernel_c_surplus<KN, kFracNone>, kSurplusCtas, kCouples, a, ac, s->tiles_c_launch);
     else
-        step_kernel_c_surplus<KN, kFracPoly><<<kSurplusCtas, kCouples, 0, s->stream>>>(a, ac, s->tiles_c_launch);
+        launch_pdl(s, step_kernel_c_surplus<KN, kFracPoly>, kSurplusCtas, kCouples, a, ac, s->tiles_c_launch);
     s->launches += 1;
 }
 
@@ -1514,6 +1531,7 @@ int psim_create(const PsimConfig* config, PsimStepper** out) {
     if (st->cfg.rebin_every == 0) st->cfg.rebin_every = 17;
     st->device = device;
     if (const char* env = getenv("PSIM_FORCE_INT_PATH")) st->force_int_path = env[0] == '1';
+    if (const char* env = getenv("PSIM_PDL")) st->pdl = env[0] == '1';
     st->rank = (int)config->slab_rank;
     st->nranks = (int)nranks;
     Grid& g = st->grid;
