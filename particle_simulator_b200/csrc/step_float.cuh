@@ -230,12 +230,14 @@ __device__ __forceinline__ void step_tile_c(const StepArgs& a, const StepArgsC& 
         const uint32_t ws = s_cs[d][rowbase + x0c] - t.p_lo[d], we = s_cs[d][rowbase + x1c + 1] - t.p_lo[d];
         // a neighbour in the row below / above sits one row distance further down / up than its own-row offset says
         const float2 ny = __fadd2_rn(ny0, splat((float)(d - 1) * pf.row_shift));
-        // (x_even, y) or (x_odd, y): the 8 bytes at offset 0 or 8 of a record
-        const float2* pj = reinterpret_cast<const float2*>(s_nb[d] + ws) + par;
-        const float2* const pj_end = reinterpret_cast<const float2*>(s_nb[d] + we);
+        // (x_even, y) or (x_odd, y): the 8 bytes at offset 0 or 8 of a record. The loop runs on the 32-bit shared-memory
+        // address itself (one add, one compare per trip; a generic pointer gets a second counter next to it)
+        uint32_t pa = smem_u32(s_nb[d] + ws) + par * 8u;
+        const uint32_t pa_end = smem_u32(s_nb[d] + we);
 #pragma unroll kPairUnroll
-        for (; pj < pj_end; pj += 2) {
-            const float2 j = *pj;
+        for (; pa < pa_end; pa += 16u) {
+            float2 j;
+            asm("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(j.x), "=f"(j.y) : "r"(pa));
             if (d == 1) pairc<KN, FRAC, true>(j.x, j.y, nx, ny, pc, gx, gy);
             else pairc<KN, FRAC, false>(j.x, j.y, nx, ny, pc, gx, gy);
         }
