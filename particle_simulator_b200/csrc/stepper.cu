@@ -83,6 +83,22 @@ struct XferOp {
 
 struct PsimGroup;
 
+// A host <-> device copy of a pipelined frame (psim_stage_frame_async, psim_download_frame_begin) issued in pieces. A slab's
+// frame makes a host round trip at every re-bin (counts over PCIe into mapped memory, a stream synchronisation, the next
+// launches); with all the ranks of a node copying 200 MB frames at once those round trips queue behind the copies and a
+// 30 ms frame takes 45 ms (170 ms under back-to-back copies: tools/diag_copy_load.py). So a slab issues one piece right
+// after each re-bin's round trip -- it is done long before the next one, 17 steps later -- and whatever is left when the
+// copy is needed. A single slab's frame makes no round trip: its copies go out whole.
+struct PacedCopy {
+    char* dst = nullptr;
+    const char* src = nullptr;
+    size_t total = 0, issued = 0, piece = 0;  // piece == 0: all at once
+    cudaMemcpyKind kind = cudaMemcpyDefault;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t done = nullptr;  // recorded behind the last piece
+    bool active = false;
+};
+
 struct FrameGraph {  // one captured frame (run_frame_with_graph)
     cudaGraphExec_t exec = nullptr;
     uint64_t steps = 0, rebins = 0, launches = 0;
@@ -163,6 +179,8 @@ struct PsimStepper {
     // pipelined download (psim_download_frame_begin / _end)
     FrameHeader* pending_dst = nullptr;
     int pending_k = -1;
+    PacedCopy paced_up, paced_down;  // the staged upload and the download in flight
+    size_t copy_piece_bytes = 0;     // 0: copies go out whole (single slab); slabs: a sixth of the copy, PSIM_COPY_PIECE_MB
     Particle* snapshot[2] = {nullptr, nullptr};  // packed snapshots of the owned particles (wire-format records)
     uint32_t ingest_cap = 0;       // records the ingest buffer holds
     unsigned char* outbox[2] = {nullptr, nullptr};
@@ -201,6 +219,7 @@ struct PsimStepper {
     uint64_t steps_executed = 0, rebins_executed = 0, launches = 0;
     std::map<uint32_t, FrameGraph> frame_graphs;  // PsimConfig.use_graph: captured frames by starting buffer parity
 
+    bool commit_pending_pump = false;
     bool timing = false;
     cudaEvent_t timing_after_main = nullptr;  // to be recorded right behind the step kernel of the launch in flight
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> timing_events;
@@ -256,6 +275,37 @@ int fail(PsimStepper* s, int code, const char* fmt, ...) {
     } while (0)
 
 inline uint32_t div_up(uint32_t a, uint32_t b) { return (a + b - 1) / b; }
+
+// Issue the next piece of a paced copy (`all`: everything that is left); the last piece is followed by its event.
+int pump_copy(PsimStepper* s, PacedCopy& c, bool all) {
+    if (!c.active) return PSIM_OK;
+    while (c.issued < c.total) {
+        const size_t n = (all || c.piece == 0) ? c.total - c.issued : std::min(c.piece, c.total - c.issued);
+        CK(cudaMemcpyAsync(c.dst + c.issued, c.src + c.issued, n, c.kind, c.stream));
+        c.issued += n;
+        if (!all && c.piece) break;
+    }
+    if (c.issued == c.total) {
+        if (c.done) CK(cudaEventRecord(c.done, c.stream));
+        c.active = false;
+    }
+    return PSIM_OK;
+}
+
+void start_copy(PsimStepper* s, PacedCopy& c, void* dst, const void* src, size_t bytes, cudaMemcpyKind kind,
+                cudaStream_t stream, cudaEvent_t done) {
+    c.dst = static_cast<char*>(dst);
+    c.src = static_cast<const char*>(src);
+    c.total = bytes;
+    c.issued = 0;
+    c.kind = kind;
+    c.stream = stream;
+    c.done = done;
+    c.active = true;
+    // a slab's frame on the reference schedule has six re-bins: a sixth of the copy behind each
+    c.piece = s->copy_piece_bytes == 1 ? std::max<size_t>((bytes + 5) / 6, (size_t)4 << 20) : s->copy_piece_bytes;
+}
+
 
 // Cubic for 2^z on z in [z_lo, z_hi] (weighted least squares on Chebyshev nodes; the constant term is
 // pinned to 1 so that z = 0 is exact). Returns the largest error of (n/m) q^(kn+fn) it causes, i.e. the
@@ -870,6 +920,7 @@ int bin_phase_commit(PsimStepper* s) {
         s->tile_hi0 = h[8];
     }
     s->ghosts_by_push = false;  // phase 4 of this binning delivers the ghost rows itself
+    s->commit_pending_pump = true;  // the next piece of the copies in flight goes out behind this binning's launches
     return PSIM_OK;
 }
 
@@ -997,6 +1048,13 @@ int team_bin(const Team& t, bool ingest, const Particle* records, uint32_t count
         s->nbr_stale = !s->float_path;  // the gather wrote the owned rows' records, the line above the ghosts'
         if ((rc = bin_phase_tiles(t.ranks[r]))) return rc;
         if (!ingest) t.ranks[r]->rebins_executed += 1;
+        if (s->commit_pending_pump) {  // the host round trip of this binning is over: the quiet 17 steps begin
+            s->commit_pending_pump = false;
+            if (!ingest) {
+                if ((rc = pump_copy(s, s->paced_down, false))) return rc;
+                if ((rc = pump_copy(s, s->paced_up, false))) return rc;
+            }
+        }
     }
     return PSIM_OK;
 }
@@ -1145,7 +1203,12 @@ int team_step(const Team& t) {
 
 int enqueue_snapshot(PsimStepper* s) {
     const int k = s->snaps_taken ? (s->snap_latest + 1) % s->nsnap : 0;
-    // the snapshot that lived in this buffer must have left it before it is overwritten
+    // the snapshot that lived in this buffer must have left it before it is overwritten: a paced download still reading it
+    // sends the rest now
+    if (s->paced_down.active && s->paced_down.src == reinterpret_cast<const char*>(s->snapshot[k])) {
+        int rc = pump_copy(s, s->paced_down, true);
+        if (rc) return rc;
+    }
     CK(cudaStreamWaitEvent(s->stream, s->snapshot_consumed[k], 0));
     const uint32_t packed = div_up(s->n, s->snapshot_stride);
     if (packed) {
@@ -1532,6 +1595,8 @@ int psim_create(const PsimConfig* config, PsimStepper** out) {
     st->device = device;
     if (const char* env = getenv("PSIM_FORCE_INT_PATH")) st->force_int_path = env[0] == '1';
     if (const char* env = getenv("PSIM_PDL")) st->pdl = env[0] == '1';
+    st->copy_piece_bytes = nranks > 1 ? 1 : 0;  // 1: a sixth of each copy (PacedCopy)
+    if (const char* env = getenv("PSIM_COPY_PIECE_MB")) st->copy_piece_bytes = (size_t)std::atoi(env) << 20;
     st->rank = (int)config->slab_rank;
     st->nranks = (int)nranks;
     Grid& g = st->grid;
@@ -1881,10 +1946,11 @@ int psim_stage_frame_async(PsimStepper* s, const FrameHeader* frame) {
         CK(cudaEventCreateWithFlags(&s->staged_ready, cudaEventDisableTiming));
     }
     // the buffer is free: the ingest that read it last returned only after its kernels had finished
-    if (frame->particle_count)
-        CK(cudaMemcpyAsync(s->staging_async, frame->particles, sizeof(Particle) * (size_t)frame->particle_count,
-                           cudaMemcpyHostToDevice, s->h2d_stream));
-    CK(cudaEventRecord(s->staged_ready, s->h2d_stream));
+    if (s->paced_up.active) return fail(s, PSIM_ESTATE, "psim_stage_frame_async: a staged frame is still on its way");
+    start_copy(s, s->paced_up, s->staging_async, frame->particles, sizeof(Particle) * (size_t)frame->particle_count,
+               cudaMemcpyHostToDevice, s->h2d_stream, s->staged_ready);
+    // whole at once for a single slab; a slab sends a piece behind each re-bin of the frame that runs meanwhile
+    if (s->copy_piece_bytes == 0 && (rc = pump_copy(s, s->paced_up, true))) return rc;
     s->staged_meta = frame->metadata;
     s->staged_count = frame->particle_count;
     s->has_staged = true;
@@ -1897,6 +1963,7 @@ int psim_upload_staged(PsimStepper* s) {
     if (rc) return rc;
     if (!s->has_staged) return fail(s, PSIM_ESTATE, "psim_upload_staged: no frame has been staged");
     CK(cudaSetDevice(s->device));
+    if ((rc = pump_copy(s, s->paced_up, true))) return rc;  // whatever the re-bins have not sent yet
     CK(cudaStreamWaitEvent(s->stream, s->staged_ready, 0));
     s->has_staged = false;
     std::swap(s->staging, s->staging_async);  // the next psim_stage_frame_async fills the other buffer
@@ -2021,12 +2088,14 @@ int psim_download_frame_begin(PsimStepper* s, uint32_t age, FrameHeader* dst) {
         return fail(s, PSIM_ECAPACITY, "psim_download_frame_begin: destination holds %u particles, snapshot has %u",
                     dst->particle_count, s->snapshot_n[k]);
     CK(cudaStreamWaitEvent(s->copy_stream, s->snapshot_ready[k], 0));
-    if (s->snapshot_n[k])
-        CK(cudaMemcpyAsync(dst->particles, s->snapshot[k], sizeof(Particle) * (size_t)s->snapshot_n[k],
-                           cudaMemcpyDeviceToHost, s->copy_stream));
-    if (s->push && s->hdr)
-        CK(cudaMemcpyAsync(&s->h_counts[15], &s->hdr->error, sizeof(uint32_t), cudaMemcpyDeviceToHost, s->copy_stream));
-    CK(cudaEventRecord(s->snapshot_consumed[k], s->copy_stream));
+    start_copy(s, s->paced_down, dst->particles, s->snapshot[k], sizeof(Particle) * (size_t)s->snapshot_n[k],
+               cudaMemcpyDeviceToHost, s->copy_stream, s->snapshot_consumed[k]);
+    // whole at once for a single slab; a slab sends nothing yet (the ingest of the next frame is about to make its round
+    // trip) and a piece behind each re-bin of the frame that follows
+    if (s->copy_piece_bytes == 0) {
+        int rc = pump_copy(s, s->paced_down, true);
+        if (rc) return rc;
+    }
     write_header(dst, s->snapshot_meta[k], s->snapshot_n[k]);  // the header is host data: valid at once
     s->pending_dst = dst;
     s->pending_k = k;
@@ -2038,6 +2107,10 @@ int psim_download_frame_end(PsimStepper* s) {
     if (!s->pending_dst) return fail(s, PSIM_ESTATE, "psim_download_frame_end: no download in flight");
     CK(cudaSetDevice(s->device));
     s->pending_dst = nullptr;
+    int rc = pump_copy(s, s->paced_down, true);
+    if (rc) return rc;
+    if (s->push && s->hdr)
+        CK(cudaMemcpyAsync(&s->h_counts[15], &s->hdr->error, sizeof(uint32_t), cudaMemcpyDeviceToHost, s->copy_stream));
     CK(cudaStreamSynchronize(s->copy_stream));
     return check_halo_error(s);
 }

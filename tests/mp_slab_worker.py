@@ -72,6 +72,35 @@ def main() -> int:
             counts_seen.add(counts)
             print(f"frame {frame}: slabs hold {counts}, identical to the single-slab run: {same}", flush=True)
             ok = ok and same and sum(counts) == n
+    # the pipelined calls on slabs (copies go out in pieces behind the re-bins): scene in, one frame, snapshot out, twice
+    from particle_simulator_b200.frame import FrameBuffer
+
+    if not meta_change:
+        piped = Stepper(wl.grid_log2, int(0.75 * n) if world > 1 else n, device=local, slab_rank=rank, slab_count=world,
+                        ingest_capacity=n, bounds=bounds, snapshot_buffers=2)
+        piped.comm_init(slabs.broadcast_bytes(dist, Stepper.comm_unique_id() if rank == 0 else None, 128))
+        outs = [FrameBuffer(int(0.75 * n) if world > 1 else n) for _ in range(2)]
+        piped.stage_async(wl.frame)
+        for k in range(2):
+            piped.upload_staged()
+            piped.stage_async(wl.frame)
+            piped.run_frame_async()
+            if k:
+                piped.download_end()
+            piped.download_begin(outs[k])
+        piped.download_end()
+        if single:
+            single.upload(wl.frame)
+            single.run_frame_async()
+            single.sync()
+        for k in range(2):
+            gathered = [None] * world if rank == 0 else None
+            dist.gather_object(outs[k].particles.tobytes(), gathered, 0)
+            if rank == 0:
+                same = b"".join(gathered) == single.download().particles.tobytes()
+                print(f"pipelined frame {k}: identical to the single-slab run: {same}", flush=True)
+                ok = ok and same
+        piped.close()
     if rank == 0 and world > 1 and len(counts_seen) < 2:
         print("no particle ever changed slab: the migration path was not exercised", flush=True)
         ok = False
