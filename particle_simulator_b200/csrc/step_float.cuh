@@ -41,8 +41,11 @@ constexpr int kCouples = 128;  // couples (= threads) per tile
 #ifndef PSIM_MIN_CTAS
 #define PSIM_MIN_CTAS 9  // CTAs per SM the register allocation aims at (56 registers per thread)
 #endif
+#ifndef PSIM_EARLY_COUPLE
+#define PSIM_EARLY_COUPLE 1  // the couple is loaded before warp 0 turns to the bulk copies (0: after, the round-1 order)
+#endif
 #ifndef PSIM_LATE_LOADS
-#define PSIM_LATE_LOADS 1
+#define PSIM_LATE_LOADS 2  // own position / velocity: 0 loaded up front, 1 after the pair loops, 2 before the last loop
 #endif
 #ifndef PSIM_OPAQUE_CONSTS
 #define PSIM_OPAQUE_CONSTS 1
@@ -153,6 +156,14 @@ __device__ __forceinline__ void step_tile_c(const StepArgs& a, const StepArgsC& 
         return;
     }
 
+#if PSIM_EARLY_COUPLE
+    // this thread's couple: the load is issued BEFORE warp 0 turns to the bulk copies, so that warp 0's own couple does not
+    // arrive a whole L2 latency after everybody else's (the other three warps were waiting for it at the barrier below:
+    // 7 % of the warp samples of the round's ncu capture)
+    uint2 cw = make_uint2(a.own_lo, t.row << g.lx);
+    if (live) cw = ac.couple_i0[t.k0 + threadIdx.x];
+#endif
+
     // TMA: the cell_start slices and the neighbour records of the three stencil rows (through L2: a ghost row is
     // written by the neighbour slab while this kernel runs). Six lanes of warp 0 issue one 1-D bulk copy each.
     if (threadIdx.x < 32) {
@@ -178,6 +189,9 @@ __device__ __forceinline__ void step_tile_c(const StepArgs& a, const StepArgsC& 
     }
 
     // this thread's couple
+#if PSIM_EARLY_COUPLE
+    const uint32_t i0 = cw.x & 0x7FFFFFFFu, has1 = cw.x >> 31, cell = cw.y;  // own_lo has no bit 31
+#else
     uint32_t i0 = a.own_lo, has1 = 0, cell = t.row << g.lx;
     if (live) {
         const uint2 w = ac.couple_i0[t.k0 + threadIdx.x];
@@ -185,6 +199,7 @@ __device__ __forceinline__ void step_tile_c(const StepArgs& a, const StepArgsC& 
         has1 = w.x >> 31;
         cell = w.y;
     }
+#endif
     const uint32_t i1 = i0 + has1;  // a half-empty couple computes its only particle twice
 #if PSIM_LATE_LOADS
     // positions and velocities are needed by the epilogue only: fetched into L1 now, read after the pair loops (eight
@@ -223,8 +238,19 @@ __device__ __forceinline__ void step_tile_c(const StepArgs& a, const StepArgsC& 
     pc.d0 = pf.d0, pc.d1 = pf.d1, pc.d2 = pf.d2, pc.d3 = pf.d3;
 #endif
     float2 gx = splat(0.f), gy = splat(0.f);
+#if PSIM_LATE_LOADS == 2
+    uint2 p0, p1;
+    float2 v0, v1;
+#endif
 #pragma unroll
     for (int d = 0; d < 3; ++d) {
+#if PSIM_LATE_LOADS == 2
+        if (d == 2) {  // the L1 prefetch above rarely survives two loops of nine CTAs (4 % of the warp samples sat at the
+                       // loads behind the loops): the real loads fly during the last loop
+            p0 = a.pos_in[i0], p1 = a.pos_in[i1];
+            v0 = a.vel[i0], v1 = a.vel[i1];
+        }
+#endif
         if (t.cs_cnt[d] == 0) continue;  // row outside the grid (uniform)
         const uint32_t rowbase = ((t.row + d - 1) << g.lx) - t.cs_lo[d];
         const uint32_t ws = s_cs[d][rowbase + x0c] - t.p_lo[d], we = s_cs[d][rowbase + x1c + 1] - t.p_lo[d];
@@ -242,7 +268,7 @@ __device__ __forceinline__ void step_tile_c(const StepArgs& a, const StepArgsC& 
             else pairc<KN, FRAC, false>(j.x, j.y, nx, ny, pc, gx, gy);
         }
     }
-#if PSIM_LATE_LOADS
+#if PSIM_LATE_LOADS == 1
     const uint2 p0 = a.pos_in[i0], p1 = a.pos_in[i1];
     const float2 v0 = a.vel[i0], v1 = a.vel[i1];
 #endif
