@@ -363,59 +363,159 @@ struct MigrantBoxHeader {
     uint32_t _pad[3];
 };
 
-__global__ void migrant_extract_kernel(const uint2* __restrict__ pos, uint32_t own_lo, uint32_t own_hi, Grid g,
-                                       uint32_t box_capacity, uint32_t* __restrict__ counters,
-                                       uint32_t* __restrict__ idx_down, uint32_t* __restrict__ idx_up,
-                                       uint32_t* __restrict__ flags) {
-    uint32_t i = own_lo + blockIdx.x * blockDim.x + threadIdx.x;
+// Migrants leave in ascending index order (the order they have in the global sorted array: what keeps slabs bit-identical
+// to a single slab). Three passes, O(n / 1024 + migrants) whatever the migration rate: count the migrants of every block of
+// 1024 consecutive particles per direction, scan the block counts, and let the blocks that have any rank theirs with ballots
+// and write them to their place in the outbox. (Round 1 appended indices with an atomic and ranked each against all others:
+// O(count^2), 2 ms for a full box.)
+constexpr uint32_t kMigBlock = 1024;
+
+__device__ __forceinline__ int migrant_dir(uint2 p, const Grid& g) {  // -1: stays, 0: down, 1: up
+    const uint32_t key = cell_of(p, g);
+    return key < kKeyUp ? -1 : (key == kKeyDown ? 0 : 1);
+}
+
+// blk_cnt[dir * nb + b]: migrants of block b (zero on entry: the pack kernel clears what it has used)
+__global__ void __launch_bounds__(kMigBlock) migrant_count_kernel(const uint2* __restrict__ pos, uint32_t own_lo, uint32_t own_hi,
+                                                                  Grid g, uint32_t nb, uint32_t* __restrict__ counters,
+                                                                  uint32_t* __restrict__ blk_cnt, uint32_t* __restrict__ flags) {
+    const uint32_t i = own_lo + blockIdx.x * kMigBlock + threadIdx.x;
     if (i >= own_hi) return;
-    uint2 p = pos[i];
-    uint32_t key = cell_of(p, g);
-    if (key < kKeyUp) return;
-    int32_t row = (int32_t)(p.y >> g.sy) - g.row_offset;
+    const uint2 p = pos[i];
+    const int dir = migrant_dir(p, g);
+    if (dir < 0) return;
+    const int32_t row = (int32_t)(p.y >> g.sy) - g.row_offset;
     // anything beyond the adjacent slabs cannot be delivered
     if (row < (int32_t)g.own_row0 - (int32_t)g.rows_below || row >= (int32_t)(g.own_row0 + g.own_rows + g.rows_above))
         atomicOr(flags, kErrMigrantTooFar);
-    uint32_t dir = key == kKeyDown ? 0u : 1u;
-    uint32_t slot = atomicAdd(&counters[dir], 1u);
-    if (slot >= box_capacity) {
-        atomicOr(flags, kErrMigrantOverflow);
-        return;
-    }
-    (dir == 0 ? idx_down : idx_up)[slot] = i;
+    atomicAdd(&counters[dir], 1u);
+    atomicAdd(&blk_cnt[(uint32_t)dir * nb + blockIdx.x], 1u);
 }
 
-__global__ void migrant_pack_kernel(const uint2* __restrict__ pos, const float2* __restrict__ vel,
-                                    const int32_t* __restrict__ ty, const uint32_t* __restrict__ counter,
-                                    const uint32_t* __restrict__ idx, uint32_t box_capacity,
-                                    unsigned char* __restrict__ box) {
-    uint32_t count = min(*counter, box_capacity);
-    MigrantBoxHeader* header = reinterpret_cast<MigrantBoxHeader*>(box);
-    Particle* rec = reinterpret_cast<Particle*>(box + sizeof(MigrantBoxHeader));
-    uint32_t e = blockIdx.x * blockDim.x + threadIdx.x;
-    if (e == 0) {
-        header->count = count;
-        header->_pad[0] = header->_pad[1] = header->_pad[2] = 0;
+// blk_off = exclusive scan of blk_cnt, per direction, and blk_list = the blocks that have migrants at all (blk_list[0] =
+// how many, then their indices in no particular order). One CTA; nb is a few thousand.
+__global__ void __launch_bounds__(1024) migrant_scan_kernel(const uint32_t* __restrict__ blk_cnt, uint32_t nb, uint32_t box_capacity,
+                                                            const uint32_t* __restrict__ counters, uint32_t* __restrict__ blk_off,
+                                                            uint32_t* __restrict__ blk_list, uint32_t* __restrict__ flags) {
+    __shared__ uint32_t s_warp[32];
+    __shared__ uint32_t s_listed;
+    if (threadIdx.x == 0) {
+        s_listed = 0;
+        if (counters[0] > box_capacity || counters[1] > box_capacity) atomicOr(flags, kErrMigrantOverflow);
     }
-    if (e >= box_capacity) return;
-    if (e >= count) {  // the rest of the box is null records (ty < 0): the receiver scans the whole box
-        Particle q;
-        q.x = q.y = 0;
-        q.vx = q.vy = 0.f;
-        q.ty = -1;
-        rec[e] = q;
+    __syncthreads();
+    const uint32_t per = (nb + 1023u) / 1024u;
+    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    for (uint32_t b = min(threadIdx.x * per, nb); b < min(threadIdx.x * per + per, nb); ++b)
+        if (blk_cnt[b] | blk_cnt[nb + b]) blk_list[1 + atomicAdd(&s_listed, 1u)] = b;
+    __syncthreads();
+    if (threadIdx.x == 0) blk_list[0] = s_listed;
+    for (uint32_t dir = 0; dir < 2; ++dir) {
+        const uint32_t* c = blk_cnt + dir * nb;
+        uint32_t* o = blk_off + dir * nb;
+        const uint32_t b0 = min(threadIdx.x * per, nb), b1 = min(b0 + per, nb);
+        uint32_t sum = 0;
+        for (uint32_t b = b0; b < b1; ++b) sum += c[b];
+        uint32_t incl = sum;
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t v = __shfl_up_sync(0xFFFFFFFFu, incl, d);
+            if ((int)lane >= d) incl += v;
+        }
+        if (lane == 31) s_warp[warp] = incl;
+        __syncthreads();
+        if (warp == 0) {
+            uint32_t w = s_warp[lane];
+            for (int d = 1; d < 32; d <<= 1) {
+                const uint32_t v = __shfl_up_sync(0xFFFFFFFFu, w, d);
+                if ((int)lane >= d) w += v;
+            }
+            s_warp[lane] = w;
+        }
+        __syncthreads();
+        uint32_t run = incl - sum + (warp ? s_warp[warp - 1] : 0u);
+        for (uint32_t b = b0; b < b1; ++b) {
+            o[b] = run;
+            run += c[b];
+        }
+        __syncthreads();
+    }
+}
+
+// CTAs [0, workers): the blocks of blk_list in turn, their migrants to their places in the two outboxes. CTAs [workers,
+// workers + ceil(capacity / 1024)): the headers and the null records (ty < 0) behind the last migrant -- the receiver scans
+// the whole box.
+__global__ void __launch_bounds__(kMigBlock) migrant_pack_kernel(const uint2* __restrict__ pos, const float2* __restrict__ vel,
+                                                                 const int32_t* __restrict__ ty, uint32_t own_lo, uint32_t own_hi,
+                                                                 Grid g, uint32_t nb, uint32_t workers,
+                                                                 const uint32_t* __restrict__ counters, uint32_t* __restrict__ blk_cnt,
+                                                                 const uint32_t* __restrict__ blk_off,
+                                                                 const uint32_t* __restrict__ blk_list, uint32_t box_capacity,
+                                                                 unsigned char* __restrict__ box_down, unsigned char* __restrict__ box_up) {
+    __shared__ uint32_t s_warp[2][32];
+    if (blockIdx.x >= workers) {
+        const uint32_t e = (blockIdx.x - workers) * kMigBlock + threadIdx.x;
+        for (int dir = 0; dir < 2; ++dir) {
+            unsigned char* box = dir ? box_up : box_down;
+            const uint32_t count = min(counters[dir], box_capacity);
+            if (e == 0) {
+                MigrantBoxHeader* header = reinterpret_cast<MigrantBoxHeader*>(box);
+                header->count = count;
+                header->_pad[0] = header->_pad[1] = header->_pad[2] = 0;
+            }
+            if (e >= count && e < box_capacity) {
+                Particle q;
+                q.x = q.y = 0;
+                q.vx = q.vy = 0.f;
+                q.ty = -1;
+                reinterpret_cast<Particle*>(box + sizeof(MigrantBoxHeader))[e] = q;
+            }
+        }
         return;
     }
-    uint32_t i = idx[e];
-    uint32_t r = 0;
-    for (uint32_t k = 0; k < count; ++k) r += idx[k] < i ? 1u : 0u;
-    Particle q;
-    uint2 p = pos[i];
-    float2 v = vel[i];
-    q.x = p.x;
-    q.y = p.y;
-    q.vx = v.x;
-    q.vy = v.y;
-    q.ty = ty[i];
-    rec[r] = q;
+    const uint32_t listed = blk_list[0];
+    for (uint32_t k = blockIdx.x; k < listed; k += workers) {
+        const uint32_t b = blk_list[1 + k];
+        const uint32_t i = own_lo + b * kMigBlock + threadIdx.x;
+        uint2 p = make_uint2(0, 0);
+        int dir = -1;
+        if (i < own_hi) {
+            p = pos[i];
+            dir = migrant_dir(p, g);
+        }
+        const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+        const uint32_t m0 = __ballot_sync(0xFFFFFFFFu, dir == 0), m1 = __ballot_sync(0xFFFFFFFFu, dir == 1);
+        if (lane == 0) {
+            s_warp[0][warp] = __popc(m0);
+            s_warp[1][warp] = __popc(m1);
+        }
+        __syncthreads();
+        if (warp == 0) {
+            for (int d = 0; d < 2; ++d) {
+                const uint32_t own = s_warp[d][lane];
+                uint32_t w = own;
+                for (int k = 1; k < 32; k <<= 1) {
+                    const uint32_t v = __shfl_up_sync(0xFFFFFFFFu, w, k);
+                    if ((int)lane >= k) w += v;
+                }
+                s_warp[d][lane] = w - own;  // exclusive
+            }
+        }
+        __syncthreads();
+        if (dir >= 0) {
+            const uint32_t below = (1u << lane) - 1u;
+            const uint32_t slot = blk_off[(uint32_t)dir * nb + b] + s_warp[dir][warp] + __popc((dir ? m1 : m0) & below);
+            if (slot < box_capacity) {
+                const float2 v = vel[i];
+                Particle q;
+                q.x = p.x;
+                q.y = p.y;
+                q.vx = v.x;
+                q.vy = v.y;
+                q.ty = ty[i];
+                reinterpret_cast<Particle*>((dir ? box_up : box_down) + sizeof(MigrantBoxHeader))[slot] = q;
+            }
+        }
+        if (threadIdx.x == 0) blk_cnt[b] = blk_cnt[nb + b] = 0;  // ready for the next re-bin
+        __syncthreads();  // s_warp is reused by the next block of the list
+    }
 }

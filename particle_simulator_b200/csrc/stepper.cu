@@ -186,7 +186,9 @@ struct PsimStepper {
     unsigned char* outbox[2] = {nullptr, nullptr};
     unsigned char* inbox[2] = {nullptr, nullptr};
     uint32_t* mig_counters = nullptr;  // 2
-    uint32_t* mig_idx[2] = {nullptr, nullptr};
+    uint32_t* mig_blk_cnt = nullptr;   // 2 x blocks of 1024 owned particles: migrants per block and direction (zero between re-bins)
+    uint32_t* mig_blk_off = nullptr;   // their exclusive scans
+    uint32_t* mig_blk_list = nullptr;  // [0] how many blocks have migrants, then which
     // halo push (HaloArgs): this slab's header, the neighbours' buffers and headers as this device sees them
     HaloHeader* hdr = nullptr;
     uint2* peer_pos[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};  // [side][buffer]
@@ -785,20 +787,20 @@ int enqueue_scan(PsimStepper* s) {
 
 // Re-bin, phase 1 (slabs only): particles that left the owned rows go into the two outboxes.
 int bin_phase_migrants(PsimStepper* s, XferOp& op) {
-    const uint32_t tb = 256;
     CK(cudaMemsetAsync(s->mig_counters, 0, 2 * sizeof(uint32_t), s->stream));
-    if (s->n) {
-        migrant_extract_kernel<<<div_up(s->n, tb), tb, 0, s->stream>>>(s->pos[s->cur_pos], s->own_lo, s->own_hi,
-                                                                       s->grid, s->box_capacity, s->mig_counters,
-                                                                       s->mig_idx[0], s->mig_idx[1], s->d_flags);
+    const uint32_t nb = div_up(s->n, kMigBlock);  // blocks of consecutive owned particles
+    if (nb) {
+        migrant_count_kernel<<<nb, kMigBlock, 0, s->stream>>>(s->pos[s->cur_pos], s->own_lo, s->own_hi, s->grid, nb, s->mig_counters,
+                                                             s->mig_blk_cnt, s->d_flags);
         s->launches += 1;
     }
-    for (int dir = 0; dir < 2; ++dir) {
-        migrant_pack_kernel<<<div_up(s->box_capacity, tb), tb, 0, s->stream>>>(
-            s->pos[s->cur_pos], s->vel[s->cur_vel], s->ty[s->cur_ty], s->mig_counters + dir, s->mig_idx[dir],
-            s->box_capacity, s->outbox[dir]);
-        s->launches += 1;
-    }
+    migrant_scan_kernel<<<1, 1024, 0, s->stream>>>(s->mig_blk_cnt, nb, s->box_capacity, s->mig_counters, s->mig_blk_off, s->mig_blk_list,
+                                                   s->d_flags);
+    const uint32_t workers = std::min(nb, 296u);  // two CTAs per SM of a B200 walk the list
+    migrant_pack_kernel<<<workers + div_up(s->box_capacity, kMigBlock), kMigBlock, 0, s->stream>>>(
+        s->pos[s->cur_pos], s->vel[s->cur_vel], s->ty[s->cur_ty], s->own_lo, s->own_hi, s->grid, nb, workers, s->mig_counters,
+        s->mig_blk_cnt, s->mig_blk_off, s->mig_blk_list, s->box_capacity, s->outbox[0], s->outbox[1]);
+    s->launches += 2;
     CK(cudaGetLastError());
     if (has_lower(s)) {
         op.send[0] = s->outbox[0];
@@ -1498,7 +1500,6 @@ void psim_destroy(PsimStepper* s) {
         cudaFree(s->ty[k]);
         cudaFree(s->outbox[k]);
         cudaFree(s->inbox[k]);
-        cudaFree(s->mig_idx[k]);
     }
     cudaFree(s->cell_start);
     cudaFree(s->pad_start);
@@ -1519,6 +1520,9 @@ void psim_destroy(PsimStepper* s) {
     cudaFree(s->snapshot[0]);
     cudaFree(s->snapshot[1]);
     cudaFree(s->mig_counters);
+    cudaFree(s->mig_blk_cnt);
+    cudaFree(s->mig_blk_off);
+    cudaFree(s->mig_blk_list);
     cudaFree(s->d_flags);
     cudaFree(s->d_counts);
     if (s->h_counts) cudaFreeHost(s->h_counts);
@@ -1658,8 +1662,14 @@ int psim_create(const PsimConfig* config, PsimStepper** out) {
         if (nranks > 1) {
             CKC(cudaMalloc(&st->outbox[k], st->box_bytes));
             CKC(cudaMalloc(&st->inbox[k], st->box_bytes));
-            CKC(cudaMalloc(&st->mig_idx[k], sizeof(uint32_t) * (size_t)st->box_capacity));
         }
+    }
+    if (nranks > 1) {
+        const size_t blocks = 2 * ((size_t)div_up((uint32_t)cap, kMigBlock) + 1);
+        CKC(cudaMalloc(&st->mig_blk_cnt, sizeof(uint32_t) * blocks));
+        CKC(cudaMemset(st->mig_blk_cnt, 0, sizeof(uint32_t) * blocks));
+        CKC(cudaMalloc(&st->mig_blk_off, sizeof(uint32_t) * blocks));
+        CKC(cudaMalloc(&st->mig_blk_list, sizeof(uint32_t) * (blocks / 2 + 1)));
     }
     CKC(cudaMalloc(&st->cell_start, sizeof(uint32_t) * ((size_t)g.cells + 1 + kPadCells)));
     // step_kernel_c needs cells of at most 2^22 fixed-point units (exact fp32 offsets within a zone / a tile's rows)

@@ -176,6 +176,24 @@ def test_particles_migrate_between_slabs(golden):
     assert len({tuple(c) for c in counts}) > 1, counts  # ownership really changed
 
 
+@pytest.mark.parametrize("drift", [2500.0, -2500.0])
+def test_thousands_of_migrants_per_rebin(drift):
+    """The whole 1M liquid drifts up (down) at 2.5 km/s: about a thousand migrants per slab boundary and re-bin (half a
+    cell row in 17 steps), ranked by the block counts + ballots of the migrant kernels. Still bit-identical to the single
+    slab, nobody lost."""
+    from particle_simulator_b200.workloads import config_1m_liquid
+
+    w = config_1m_liquid()
+    w.frame.metadata["steps_per_frame"] = 52  # 52 steps, 3 re-bins
+    w.frame.particles["vy"] += np.float32(drift)
+    sent = 0
+    for single, group, gr in run_both(w.frame, w.grid_log2, 8, frames=2, per_slab_capacity=w.particles // 2):
+        assert single.tobytes() == group.tobytes()
+        assert sum(s.particle_count for s in gr.slabs) == w.particles
+        sent = sum(s.migrants_sent for s in gr.slabs)
+    assert sent > 10000, sent
+
+
 def test_liquid_1m_in_8_slabs():
     """configs[1]-sized: 1M particles melting at 150-250 m/s, 1024x1024 cells, 8 slabs of 128 rows."""
     from particle_simulator_b200.workloads import config_1m_liquid
