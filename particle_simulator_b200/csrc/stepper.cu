@@ -308,9 +308,13 @@ void start_copy(PsimStepper* s, PacedCopy& c, void* dst, const void* src, size_t
     c.active = true;
     // a slab's frame on the reference schedule has six re-bins: a sixth of the copy behind each
     c.piece = s->copy_piece_bytes == 1 ? std::max<size_t>((bytes + 5) / 6, (size_t)4 << 20) : s->copy_piece_bytes;
-    // paced by the steps instead: a 96th behind every step of the frame that runs meanwhile (a frame has 101)
-    if (s->copy_pace_steps && s->copy_piece_bytes <= 1)  // PSIM_COPY_PIECE_MB keeps its say
-        c.piece = std::max<size_t>(((bytes + 95) / 96 + 255) & ~(size_t)255, (size_t)256 << 10);
+    // paced by the steps instead: a piece behind every step of the frame that runs meanwhile, done a few steps before its
+    // end (a frame of the benchmark has 101 steps: 96 pieces)
+    if (s->copy_pace_steps && s->copy_piece_bytes <= 1) {  // PSIM_COPY_PIECE_MB keeps its say
+        const size_t steps = s->meta.steps_per_frame;
+        const size_t parts = std::min<size_t>(96, steps > 5 ? steps - 5 : 1);
+        c.piece = std::max<size_t>(((bytes + parts - 1) / parts + 255) & ~(size_t)255, (size_t)256 << 10);
+    }
 }
 
 // Slabs: the copies in flight advance by one small piece per step, each piece ordered behind that step on the device (an
