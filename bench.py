@@ -412,6 +412,12 @@ def run_ours(args, rank: int, world: int, local_rank: int) -> None:
                                     rows_per_slab_log2=rows_log2, grid_x_log2=13)
         st = Stepper(wl.grid_log2, int(1.05 * per_slab) + 65536, device=local_rank, slab_rank=rank, slab_count=world,
                      ingest_capacity=wl.frame.count, snapshot_buffers=2, use_graph=world == 1)
+    elif args.workload == "liquid":
+        # BASELINE.json configs[1]: the 1M-particle liquid-density box on 1024^2 cells, one GPU
+        if world != 1:
+            raise SystemExit("--workload liquid is the single-GPU configuration (BASELINE.json configs[1])")
+        wl = workloads.config_1m_liquid(storage=pinned_frame_storage(1000 * 1000))
+        st = Stepper(wl.grid_log2, wl.particles, device=local_rank, snapshot_buffers=2, use_graph=True)
     elif world == 1:
         wl = workloads.config_10m_solid(storage=pinned_frame_storage(3162 * 3163))
         st = Stepper(wl.grid_log2, wl.particles, device=local_rank, snapshot_buffers=2, use_graph=True)
@@ -553,6 +559,9 @@ def run_ours(args, rank: int, world: int, local_rank: int) -> None:
         achieved = ALGO_BYTES_PER_UPDATE * n_local / (kernel_ms * 1e-3) / 1e9  # per GPU (rank 0's slab)
         traffic, traffic_note = recorded_traffic()
         config = base_config(wl.name, wl.description, n)
+        if args.workload == "liquid":
+            config["l2"] = ("state (1M x (20 B + 16 B of neighbour record) x 2 buffers = 72 MB) FITS the 126 MB L2 and is not flushed "
+                            "between frames (a frame is 101 dependent steps): an L2-resident configuration, not the metric's")
         if world > 1 or strong or clustered:
             config["particles_rank0"] = n_local
             config["decomposition"] = ("single slab" if world == 1 else
@@ -594,7 +603,7 @@ def run_ours(args, rank: int, world: int, local_rank: int) -> None:
         if world > 1 or clustered:
             line["balance"] = {"particles_per_slab_max_over_mean": held[0] / (held[1] / world),
                                "migrants_per_rebin": migrants / max(rebins_total, 1), "rebins": rebins_total}
-        if world == 1 and not strong and not clustered:
+        if world == 1 and not strong and not clustered and args.workload == "solid":
             st.close()
             if not args.no_phases:
                 solid = {"phase": "solid", "particles": n_local, "kernel_ms": kernel_ms, "achieved": achieved,
@@ -617,8 +626,9 @@ def main() -> None:
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
     ap.add_argument("--ref-steps", type=int, default=18,
                     help="--impl reference: steps_per_frame of one bench step (18 = one re-bin cycle of the schedule)")
-    ap.add_argument("--workload", choices=["solid", "clustered"], default="solid",
-                    help="solid (default): the metric's 10M-particle lattice; clustered: BASELINE.json configs[4], droplets + gas "
+    ap.add_argument("--workload", choices=["solid", "liquid", "clustered"], default="solid",
+                    help="solid (default): the metric's 10M-particle lattice; liquid: BASELINE.json configs[1], the 1M-particle "
+                         "liquid box on one GPU; clustered: BASELINE.json configs[4], droplets + gas "
                          "of two species, rows cut by psim_balance_rows")
     ap.add_argument("--cluster-side", type=int, default=1200, help="--workload clustered: droplets of side x side particles")
     ap.add_argument("--equal-rows", action="store_true", help="--workload clustered: equal rows per slab instead of balanced")
