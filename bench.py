@@ -84,6 +84,9 @@ class ClockSampler:
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.15)
+        t0 = time.perf_counter()
+        while not self.rows and time.perf_counter() - t0 < 1.0:  # a region shorter than nvidia-smi's first sample
+            time.sleep(0.05)
         self.proc.terminate()
         try:
             self.proc.wait(timeout=2)

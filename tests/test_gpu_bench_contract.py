@@ -33,7 +33,8 @@ def test_bench_line_has_the_contract_keys():
     assert r["frac"] == pytest.approx(r["achieved"] / r["peak"], rel=1e-9)
     assert r["achieved"] == pytest.approx(40 * n / (r["kernel_ms"] * 1e-3) / 1e9, rel=1e-6)  # 40 algorithmic bytes per update
     e = d["e2e"]
-    assert e["unit"] == d["unit"] and 0 < e["value"] <= 1.05 * d["value"]
+    assert e["unit"] == d["unit"] and 0 < e["value"] <= 1.2 * d["value"]  # two 4 ms frames: noisy, but the same order
     assert e["h2d_bytes_per_step"] >= 20 * n and e["d2h_bytes_per_step"] >= 20 * n  # a 20-byte record each way, every step
     assert d["gpu_launches"] >= 2 * steps  # our own kernels ran inside the timed region
-    assert d["clocks"]["sm_mhz"] > 0 and "reasons" in d["clocks"]
+    assert "sm_mhz" in d["clocks"] and "sm_max_mhz" in d["clocks"] and isinstance(d["clocks"]["reasons"], list)
+    assert d["clocks"]["sm_mhz"] is None or d["clocks"]["sm_mhz"] > 0  # None only if nvidia-smi gave no sample at all
